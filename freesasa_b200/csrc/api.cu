@@ -1,0 +1,508 @@
+// freesasa_b200/csrc/api.cu — contexts, device scratch management and the C ABI (include/fsb200.h).
+//
+// The host side here is deliberately thin: validate, upload, enqueue the fixed kernel sequence
+// (cells.cu, integrate.cu), read back one status block together with the results, and only in the
+// rare large-neighbourhood case run a second pass.  There is no CPU implementation of the hot path
+// in this library: if no sm_100 device is usable every compute entry point fails with a message.
+#include "../../include/fsb200.h"
+#include "engine.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace fsb200;
+
+namespace {
+
+thread_local char g_error[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return FSB200_FAIL;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = need + need / 4 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct fsb200_ctx {
+    int device = 0;
+    int precision = FSB200_FP32;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int *h_status = nullptr;  // pinned, kCtrCount ints
+    int grid_ctas[2][2] = {{0, 0}, {0, 0}};
+    fsb200_stats stats{};
+    std::mutex lock;
+
+    // inputs / outputs when the caller hands us host memory
+    DevBuf<double> in_xyz, in_radii, out_sasa;
+    DevBuf<int> out_nn;
+    // workspace
+    DevBuf<int> offsets, cell_of, cell_start, cell_fill, slot_atom, perm, scan_tmp, counters, overflow;
+    DevBuf<unsigned long long> bounds;
+    DevBuf<GridDesc> grid;
+    DevBuf<double4> atoms;
+    DevBuf<Item> items;
+    DevBuf<unsigned char> scratch;
+    // Shrake-Rupley test points of the last resolution used
+    int sr_points = 0;
+    DevBuf<float4> points_f;
+    DevBuf<double> points_d;
+    int last_n = 0;  // atoms of the last device call (for unpermute)
+};
+
+namespace {
+
+// Golden-spiral unit vectors, generated with the recurrence of the reference (src/sasa_sr.c:56-90:
+// z and the longitude are ACCUMULATED) so that the fp64 re-check sees bit-identical points.
+void make_test_points(int n, std::vector<double> &pd, std::vector<float4> &pf)
+{
+    pd.resize(3 * (size_t)n);
+    pf.resize(n);
+    const double dlong = M_PI * (3 - std::sqrt(5.0)), dz = 2.0 / n;
+    double longitude = 0, z = 1 - dz / 2;
+    for (int k = 0; k < n; ++k) {
+        const double r = std::sqrt(1 - z * z);
+        pd[3 * k] = std::cos(longitude) * r;
+        pd[3 * k + 1] = std::sin(longitude) * r;
+        pd[3 * k + 2] = z;
+        pf[k] = make_float4((float)pd[3 * k], (float)pd[3 * k + 1], (float)pd[3 * k + 2], 0.f);
+        z -= dz;
+        longitude += dlong;
+    }
+}
+
+int ensure_workspace(fsb200_ctx *c, int n, int n_struct, Workspace &ws)
+{
+    const size_t cells = (size_t)kCellsPerAtomCap * n + (size_t)kCellsSlack * n_struct;
+    if (cells + 1 > 0x7fffffffull) return fail("problem too large: %d atoms in %d structures", n, n_struct);
+    CU(c->offsets.ensure((size_t)n_struct + 1));
+    CU(c->bounds.ensure(7 * (size_t)n_struct));
+    CU(c->grid.ensure(n_struct));
+    CU(c->cell_of.ensure(n));
+    CU(c->cell_start.ensure(cells + 1));
+    CU(c->cell_fill.ensure(cells));
+    CU(c->slot_atom.ensure(n));
+    CU(c->atoms.ensure(n));
+    CU(c->perm.ensure(n));
+    CU(c->items.ensure(n));
+    CU(c->scan_tmp.ensure(cells / 2048 + 2));
+    CU(c->counters.ensure(kCtrCount));
+    CU(c->overflow.ensure(n));
+    ws.n = n;
+    ws.n_struct = n_struct;
+    ws.offsets = c->offsets.p;
+    ws.bounds = c->bounds.p;
+    ws.grid = c->grid.p;
+    ws.total_cells_cap = (int)cells;
+    ws.cell_of = c->cell_of.p;
+    ws.cell_start = c->cell_start.p;
+    ws.cell_fill = c->cell_fill.p;
+    ws.slot_atom = c->slot_atom.p;
+    ws.atoms = c->atoms.p;
+    ws.perm = c->perm.p;
+    ws.items = c->items.p;
+    ws.scan_tmp = c->scan_tmp.p;
+    ws.counters = c->counters.p;
+    ws.overflow = c->overflow.p;
+    return FSB200_SUCCESS;
+}
+
+int ensure_points(fsb200_ctx *c, int n_points, cudaStream_t stream)
+{
+    if (c->sr_points == n_points) return FSB200_SUCCESS;
+    std::vector<double> pd;
+    std::vector<float4> pf;
+    make_test_points(n_points, pd, pf);
+    CU(c->points_d.ensure(pd.size()));
+    CU(c->points_f.ensure(pf.size()));
+    CU(cudaMemcpyAsync(c->points_d.p, pd.data(), pd.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(c->points_f.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));  // the host vectors die here
+    c->sr_points = n_points;
+    return FSB200_SUCCESS;
+}
+
+struct Request {
+    int alg, resolution;
+    double probe;
+    int n, n_struct;
+    const int *h_offsets;  // n_struct+1, or nullptr for one structure
+    const double *d_xyz, *d_radii;
+    double *d_out;
+    int *d_nn;             // optional
+    int shard_index, shard_count;
+    cudaStream_t stream;
+};
+
+// Enqueue the whole pipeline.  `after_enqueue` (may be null) lets the host-buffer entry points queue
+// their result download before the one synchronisation of the call.
+template <typename F>
+int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
+{
+    if (rq.alg != FSB200_LEE_RICHARDS && rq.alg != FSB200_SHRAKE_RUPLEY) return fail("unknown algorithm %d", rq.alg);
+    if (rq.n <= 0) return fail("no atoms");
+    if (rq.resolution <= 0) return fail("invalid resolution %d, must be > 0", rq.resolution);
+    if (!std::isfinite(rq.probe) || rq.probe < 0) return fail("invalid probe radius %f", rq.probe);
+    if (rq.shard_count < 1 || rq.shard_index < 0 || rq.shard_index >= rq.shard_count) return fail("invalid shard %d of %d", rq.shard_index, rq.shard_count);
+    cudaStream_t st = rq.stream;
+    Workspace ws;
+    if (ensure_workspace(c, rq.n, rq.n_struct, ws)) return FSB200_FAIL;
+    ws.xyz = rq.d_xyz;
+    ws.radii = rq.d_radii;
+    ws.probe = rq.probe;
+    if (rq.n_struct > 1)
+        CU(cudaMemcpyAsync(ws.offsets, rq.h_offsets, sizeof(int) * ((size_t)rq.n_struct + 1), cudaMemcpyHostToDevice, st));
+
+    IntegrateArgs ia{};
+    ia.alg = rq.alg;
+    ia.resolution = rq.resolution;
+    ia.precision = c->precision;
+    ia.shard_begin = fsb200_shard_begin(rq.n, rq.shard_index, rq.shard_count);
+    ia.shard_end = fsb200_shard_end(rq.n, rq.shard_index, rq.shard_count);
+    ia.sorted_output = rq.shard_count > 1;
+    ia.out = rq.d_out;
+    ia.nn_out = rq.d_nn;
+    if (rq.alg == FSB200_SHRAKE_RUPLEY) {
+        if (ensure_points(c, rq.resolution, st)) return FSB200_FAIL;
+        ia.points_f = c->points_f.p;
+        ia.points_d = c->points_d.p;
+    }
+    int &ctas = c->grid_ctas[rq.alg][c->precision];
+    if (ctas == 0) ctas = integrate_grid_ctas(rq.alg, c->precision, c->device);
+    ia.grid_ctas = ctas;
+
+    int launches = 0;
+    CU(cudaEventRecord(c->ev[0], st));
+    launches += launch_cell_build(ws, st);
+    CU(cudaEventRecord(c->ev[1], st));
+    launches += launch_integrate(ws, ia, st);
+    CU(cudaEventRecord(c->ev[2], st));
+    CU(cudaMemcpyAsync(c->h_status, ws.counters, sizeof(int) * kCtrCount, cudaMemcpyDeviceToHost, st));
+    if (after_enqueue(st)) return FSB200_FAIL;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    c->last_n = rq.n;
+
+    fsb200_stats &s = c->stats;
+    s.n_atoms = rq.n;
+    s.n_structures = rq.n_struct;
+    s.n_items = c->h_status[kCtrItems];
+    s.n_overflow = c->h_status[kCtrOverflow];
+    s.max_neighbours = 0;
+    if (c->h_status[kCtrBadInput]) {
+        g_launches += launches;
+        return fail("non-finite coordinate or radius in input");
+    }
+    float overflow_ms = 0.f;
+    cudaEventElapsedTime(&s.device_ms, c->ev[0], c->ev[2]);
+    cudaEventElapsedTime(&s.integrate_ms, c->ev[1], c->ev[2]);
+    if (s.n_overflow > 0) {
+        // Large neighbourhoods (more than kNbCap neighbours): second pass with the lists in global memory.
+        const int cap = ((c->h_status[kCtrMaxCand] + 7) / 8) * 8;
+        s.max_neighbours = c->h_status[kCtrMaxCand];
+        const int warps = overflow_warps(s.n_overflow);
+        CU(c->scratch.ensure(overflow_scratch_bytes(warps, cap, c->precision)));
+        CU(cudaEventRecord(c->ev[0], st));  // ev[0]/ev[2] of the first pass were consumed above
+        launches += launch_overflow(ws, ia, s.n_overflow, cap, c->scratch.p, st);
+        CU(cudaEventRecord(c->ev[3], st));
+        if (after_enqueue(st)) return FSB200_FAIL;
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        cudaEventElapsedTime(&overflow_ms, c->ev[0], c->ev[3]);
+    }
+    s.device_ms += overflow_ms;
+    s.kernel_launches = launches;
+    g_launches += launches;
+    return FSB200_SUCCESS;
+}
+
+// ---- context pool for the context-free entry points ---------------------------------------------------
+std::mutex g_pool_lock;
+std::vector<fsb200_ctx *> g_pool;  // idle contexts (any device)
+
+fsb200_ctx *pool_acquire()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        fail("no CUDA device available: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    {
+        std::lock_guard<std::mutex> g(g_pool_lock);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i]->device == dev) {
+                fsb200_ctx *c = g_pool[i];
+                g_pool.erase(g_pool.begin() + i);
+                return c;
+            }
+    }
+    return fsb200_ctx_create(dev);
+}
+
+void pool_release(fsb200_ctx *c)
+{
+    std::lock_guard<std::mutex> g(g_pool_lock);
+    g_pool.push_back(c);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *fsb200_last_error(void) { return g_error; }
+const char *fsb200_version(void) { return "fsb200 0.1 (sm_100a)"; }
+unsigned long long fsb200_launch_count(void) { return g_launches.load(); }
+
+int fsb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fsb200_available(void)
+{
+    const int n = fsb200_device_count();
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) return 1;
+    }
+    return 0;
+}
+
+int fsb200_shard_begin(int n_total, int shard_index, int shard_count)
+{
+    return (int)(((long long)n_total * shard_index) / shard_count);
+}
+int fsb200_shard_end(int n_total, int shard_index, int shard_count)
+{
+    return (int)(((long long)n_total * (shard_index + 1)) / shard_count);
+}
+
+fsb200_ctx *fsb200_ctx_create(int device)
+{
+    int n = fsb200_device_count();
+    if (device < 0 || device >= n) {
+        fail("CUDA device %d not available (%d visible): the engine has no CPU path", device, n);
+        return nullptr;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) {
+        fail("device %d has compute capability %d.x; this library contains sm_100a code only", device, major);
+        return nullptr;
+    }
+    DeviceGuard guard(device);
+    fsb200_ctx *c = new fsb200_ctx();
+    c->device = device;
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&c->h_status, sizeof(int) * kCtrCount) == cudaSuccess;
+    if (!ok) {
+        fail("could not initialise context on device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        fsb200_ctx_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void fsb200_ctx_destroy(fsb200_ctx *c)
+{
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->in_xyz.release(); c->in_radii.release(); c->out_sasa.release(); c->out_nn.release();
+    c->offsets.release(); c->cell_of.release(); c->cell_start.release(); c->cell_fill.release();
+    c->slot_atom.release(); c->perm.release(); c->scan_tmp.release(); c->counters.release();
+    c->overflow.release(); c->bounds.release(); c->grid.release(); c->atoms.release();
+    c->items.release(); c->scratch.release(); c->points_f.release(); c->points_d.release();
+    for (int k = 0; k < 4; ++k)
+        if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fsb200_ctx_set_precision(fsb200_ctx *c, int precision)
+{
+    if (!c) return fail("null context");
+    if (precision != FSB200_FP32 && precision != FSB200_FP64) return fail("unknown precision %d", precision);
+    c->precision = precision;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ctx_stats(const fsb200_ctx *c, fsb200_stats *out)
+{
+    if (!c || !out) return fail("null argument");
+    *out = c->stats;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_atoms, const double *const *xyz,
+                          const double *const *radii, double *const *sasa, double probe, int resolution)
+{
+    if (!c) return fail("null context");
+    if (n_struct <= 0 || !n_atoms || !xyz || !radii || !sasa) return fail("invalid batch arguments");
+    std::lock_guard<std::mutex> g(c->lock);
+    DeviceGuard guard(c->device);
+    std::vector<int> off((size_t)n_struct + 1, 0);
+    for (int k = 0; k < n_struct; ++k) {
+        if (n_atoms[k] <= 0 || !xyz[k] || !radii[k] || !sasa[k]) return fail("structure %d is empty or has a null array", k);
+        if ((long long)off[k] + n_atoms[k] > 0x3fffffffll) return fail("batch too large");
+        off[k + 1] = off[k] + n_atoms[k];
+    }
+    const int n = off[n_struct];
+    CU(c->in_xyz.ensure(3 * (size_t)n));
+    CU(c->in_radii.ensure(n));
+    CU(c->out_sasa.ensure(n));
+    cudaStream_t st = c->stream;
+    for (int k = 0; k < n_struct; ++k) {
+        CU(cudaMemcpyAsync(c->in_xyz.p + 3 * (size_t)off[k], xyz[k], sizeof(double) * 3 * (size_t)n_atoms[k], cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->in_radii.p + off[k], radii[k], sizeof(double) * (size_t)n_atoms[k], cudaMemcpyHostToDevice, st));
+    }
+    Request rq{alg, resolution, probe, n, n_struct, off.data(), c->in_xyz.p, c->in_radii.p, c->out_sasa.p, nullptr, 0, 1, st};
+    auto download = [&](cudaStream_t s) -> int {
+        for (int k = 0; k < n_struct; ++k)
+            CU(cudaMemcpyAsync(sasa[k], c->out_sasa.p + off[k], sizeof(double) * (size_t)n_atoms[k], cudaMemcpyDeviceToHost, s));
+        return FSB200_SUCCESS;
+    };
+    return run_pipeline(c, rq, download);
+}
+
+int fsb200_ctx_calc(fsb200_ctx *c, int alg, double *sasa, const double *xyz, const double *radii, int n, double probe,
+                    int resolution)
+{
+    if (!sasa || !xyz || !radii) return fail("null array");
+    return fsb200_ctx_calc_batch(c, alg, 1, &n, &xyz, &radii, &sasa, probe, resolution);
+}
+
+int fsb200_ctx_neighbour_counts(fsb200_ctx *c, int *counts, const double *xyz, const double *radii, int n, double probe)
+{
+    if (!c || !counts || !xyz || !radii || n <= 0) return fail("invalid arguments");
+    std::lock_guard<std::mutex> g(c->lock);
+    DeviceGuard guard(c->device);
+    CU(c->in_xyz.ensure(3 * (size_t)n));
+    CU(c->in_radii.ensure(n));
+    CU(c->out_sasa.ensure(n));
+    CU(c->out_nn.ensure(n));
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->in_xyz.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->in_radii.p, radii, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    Request rq{FSB200_LEE_RICHARDS, 1, probe, n, 1, nullptr, c->in_xyz.p, c->in_radii.p, c->out_sasa.p, c->out_nn.p, 0, 1, st};
+    auto download = [&](cudaStream_t s) -> int {
+        CU(cudaMemcpyAsync(counts, c->out_nn.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        return FSB200_SUCCESS;
+    };
+    return run_pipeline(c, rq, download);
+}
+
+int fsb200_ctx_calc_device(fsb200_ctx *c, int alg, const double *d_xyz, const double *d_radii, int n_total, int n_struct,
+                           const int *offsets, double probe, int resolution, int shard_index, int shard_count,
+                           double *d_sasa, void *stream)
+{
+    if (!c || !d_xyz || !d_radii || !d_sasa) return fail("null argument");
+    if (n_struct < 1 || (n_struct > 1 && !offsets)) return fail("offsets required for %d structures", n_struct);
+    if (n_struct > 1 && shard_count > 1) return fail("sharding applies to a single replicated structure");
+    if (n_struct > 1 && (offsets[0] != 0 || offsets[n_struct] != n_total)) return fail("offsets do not span the atoms");
+    std::lock_guard<std::mutex> g(c->lock);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    Request rq{alg, resolution, probe, n_total, n_struct, offsets, d_xyz, d_radii, d_sasa, nullptr, shard_index, shard_count, st};
+    return run_pipeline(c, rq, [](cudaStream_t) { return FSB200_SUCCESS; });
+}
+
+int fsb200_ctx_unpermute(fsb200_ctx *c, const double *d_sorted, double *d_out, int n_total, void *stream)
+{
+    if (!c || !d_sorted || !d_out) return fail("null argument");
+    if (n_total != c->last_n) return fail("unpermute: %d atoms but the last call had %d", n_total, c->last_n);
+    std::lock_guard<std::mutex> g(c->lock);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    g_launches += launch_unpermute(c->perm.p, d_sorted, d_out, n_total, st);
+    CU(cudaStreamSynchronize(st));
+    return FSB200_SUCCESS;
+}
+
+// ---- context-free drop-in entry points ------------------------------------------------------------------
+int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
+                      double *const *sasa, double probe, int resolution)
+{
+    fsb200_ctx *c = pool_acquire();
+    if (!c) return FSB200_FAIL;
+    const int rc = fsb200_ctx_calc_batch(c, alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
+    pool_release(c);
+    return rc;
+}
+
+int fsb200_lr(double *sasa, const double *xyz, const double *radii, int n, double probe, int n_slices)
+{
+    if (!sasa || !xyz || !radii) return fail("null array");
+    return fsb200_calc_batch(FSB200_LEE_RICHARDS, 1, &n, &xyz, &radii, &sasa, probe, n_slices);
+}
+
+int fsb200_sr(double *sasa, const double *xyz, const double *radii, int n, double probe, int n_points)
+{
+    if (!sasa || !xyz || !radii) return fail("null array");
+    return fsb200_calc_batch(FSB200_SHRAKE_RUPLEY, 1, &n, &xyz, &radii, &sasa, probe, n_points);
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// freesasa_b200/csrc/engine.cuh — shared declarations of the B200 SASA engine (sm_100a only).
+//
+// Pipeline of one call (all device-driven: no host round trip between the upload and the
+// download; every buffer is sized from the atom count alone):
+//
+//   bounds   per-structure min/max/maxR            (replaces reference src/nb.c:43-72,242-254)
+//   grid     per-structure cell edge + dimensions  (src/nb.c:55-71,543)
+//   count    cell id per atom, histogram            (src/nb.c:133-175)
+//   scan     exclusive scan of the histogram  ->  cell_start
+//   scatter  atoms to their cell's slot range
+//   reorder  deterministic order inside each cell, pack {x,y,z,R} as double4, emit work items
+//   integrate  persistent kernel: per work item, TMA-stage the 27-cell neighbourhood into shared
+//            memory, one warp per atom: exact fp64 neighbour test (src/nb.c:483-491), then
+//            Lee-Richards slices (src/sasa_lr.c:270-408) or Shrake-Rupley test points
+//            (src/sasa_sr.c:276-338) in the atom-local frame
+//
+// No global adjacency is ever materialised (the reference's nb_list is ~3.5 KB/atom).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fsb200 {
+
+constexpr int kWarpsPerCta = 8;             // one atom per warp, one work item = up to 8 atoms of a cell
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr int kItemAtoms = kWarpsPerCta;
+constexpr int kTileCap = 768;               // atoms of the 27-cell neighbourhood staged in smem (24 KB)
+constexpr int kNbCap = 160;                 // per-warp neighbour list capacity in smem
+constexpr int kCellsPerAtomCap = 2;         // grid budget: cells <= 2*n_k + 64 per structure
+constexpr int kCellsSlack = 64;
+
+// Per-structure uniform grid, computed on the device.
+struct GridDesc {
+    double lo[3];
+    double edge;      // >= 2*max(R) (slightly padded); grown if the box would need too many cells
+    int dim[3];
+    int cell_base;    // first global cell id of this structure (= 2*atom_begin + 64*sid)
+    int atom_begin;
+    int atom_end;
+};
+
+// One unit of work for the integration kernel: <= kItemAtoms consecutive atoms of one cell.
+struct Item {
+    int sid;      // structure
+    int cell;     // cell id local to the structure
+    int first;    // first sorted position
+    int count;    // atoms in this item
+};
+
+// Device-side counters / status of one call (one 64-int block, zeroed per call).
+enum CounterSlot {
+    kCtrItems = 0,      // number of work items produced by reorder
+    kCtrQueue = 1,      // work queue head of the integration kernel
+    kCtrOverflow = 2,   // atoms whose neighbour list did not fit kNbCap
+    kCtrMaxCand = 3,    // max candidate count among overflow atoms
+    kCtrBadInput = 4,   // non-finite coordinate or radius seen
+    kCtrQueue2 = 5,     // queue head of the overflow kernel
+    kCtrCount = 16
+};
+
+struct Workspace {
+    // inputs (device)
+    const double *xyz = nullptr;    // 3n AoS
+    const double *radii = nullptr;  // n, without probe
+    int n = 0;
+    int n_struct = 1;
+    double probe = 0;
+    // per-structure
+    int *offsets = nullptr;                 // n_struct+1
+    unsigned long long *bounds = nullptr;   // 7 per structure, order-preserving encoding of doubles
+    GridDesc *grid = nullptr;
+    // per-atom / per-cell
+    int total_cells_cap = 0;
+    int *cell_of = nullptr;      // n     global cell id of each atom (caller order)
+    int *cell_start = nullptr;   // total_cells_cap + 1  histogram -> exclusive scan
+    int *cell_fill = nullptr;    // total_cells_cap
+    int *slot_atom = nullptr;    // n     atom index by slot (unordered inside a cell)
+    double4 *atoms = nullptr;    // n     sorted {x,y,z,R=r+probe}
+    int *perm = nullptr;         // n     sorted position -> caller index
+    Item *items = nullptr;       // n
+    int *scan_tmp = nullptr;     // block sums for the scan
+    int *counters = nullptr;     // kCtrCount ints
+    int *overflow = nullptr;     // n     sorted positions of overflow atoms
+};
+
+struct IntegrateArgs {
+    int alg;              // 0 LR, 1 SR
+    int resolution;       // slices or points
+    int precision;        // 0 fp32, 1 fp64
+    int shard_begin;      // only items with first in [shard_begin, shard_end) are integrated
+    int shard_end;
+    int sorted_output;    // 1: out[sorted pos], 0: out[perm[pos]]
+    double *out;          // n doubles
+    int *nn_out;          // optional neighbour counts (caller order), or nullptr
+    const float4 *points_f;   // SR: unit test points, float
+    const double *points_d;   // SR: unit test points, 3*resolution doubles (bit-identical to the reference's)
+    int grid_ctas;
+};
+
+// cells.cu
+int launch_cell_build(const Workspace &ws, cudaStream_t stream);   // returns number of launches
+// integrate.cu
+int launch_integrate(const Workspace &ws, const IntegrateArgs &args, cudaStream_t stream);
+int launch_overflow(const Workspace &ws, const IntegrateArgs &args, int n_overflow, int list_cap,
+                    void *scratch, cudaStream_t stream);
+size_t overflow_scratch_bytes(int n_warps, int list_cap, int precision);
+int overflow_warps(int n_overflow);
+int integrate_grid_ctas(int alg, int precision, int device);
+int launch_unpermute(const int *perm, const double *sorted, double *out, int n, cudaStream_t stream);
+
+// ---- small device helpers --------------------------------------------------------------------
+// order-preserving map double -> uint64 so min/max can use integer atomics
+__host__ __device__ inline unsigned long long encode_ordered(double v)
+{
+    unsigned long long b;
+#ifdef __CUDA_ARCH__
+    b = (unsigned long long)__double_as_longlong(v);
+#else
+    union { double d; unsigned long long u; } c; c.d = v; b = c.u;
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double decode_ordered(unsigned long long k)
+{
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    union { double d; unsigned long long u; } c; c.u = b; return c.d;
+#endif
+}
+
+__host__ __device__ __forceinline__ int cell_cap_base(int atom_begin, int sid)
+{
+    return kCellsPerAtomCap * atom_begin + kCellsSlack * sid;
+}
+
+// structure owning caller-order atom i (offsets[sid] <= i < offsets[sid+1])
+__device__ __forceinline__ int find_structure(const int *offsets, int n_struct, int i)
+{
+    int lo = 0, hi = n_struct;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Cell coordinates of a point.  Division (not multiplication by a reciprocal) so that the cell
+// of an atom is a monotone function of its coordinate with exactly the edge as period.
+__device__ __forceinline__ void cell_coords(const GridDesc &g, double x, double y, double z, int c[3])
+{
+    int ix = (int)((x - g.lo[0]) / g.edge), iy = (int)((y - g.lo[1]) / g.edge), iz = (int)((z - g.lo[2]) / g.edge);
+    c[0] = min(max(ix, 0), g.dim[0] - 1);
+    c[1] = min(max(iy, 0), g.dim[1] - 1);
+    c[2] = min(max(iz, 0), g.dim[2] - 1);
+}
+
+}  // namespace fsb200

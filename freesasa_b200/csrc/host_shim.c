@@ -1,0 +1,235 @@
+/* freesasa_b200/csrc/host_shim.c — C host layer: the reference's hot-path entry points on top of
+ * the fsb200 C ABI (include/fsb200.h).  See include/freesasa_b200_host.h.
+ *
+ * What stays identical to the reference (so existing callers and tests keep working):
+ *   - freesasa_calc() allocates the result with malloc, dispatches on parameters->alg, frees the
+ *     result and returns NULL when the engine reports FREESASA_FAIL, sums `total` serially in atom
+ *     order and copies the parameters (src/freesasa.c:76-120);
+ *   - freesasa_lee_richards()/freesasa_shrake_rupley() validate like src/sasa_lr.c:169-193 and
+ *     src/sasa_sr.c:173-200: more than 16 threads -> FAIL, resolution <= 0 -> FAIL, zero atoms ->
+ *     WARN, more threads than atoms -> warning and carry on;
+ *   - messages go to the error stream selected with freesasa_set_err_out() and obey the verbosity.
+ * What changes: the numeric work is one call into the GPU engine; n_threads is validated but does
+ * not drive anything.  There is no CPU fallback: if the engine fails, the message says why.
+ */
+#include "freesasa_b200_host.h"
+#include "fsb200.h"
+
+#include <assert.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAX_THREADS 16 /* MAX_LR_THREADS / MAX_SR_THREADS, src/sasa_lr.c:17, src/sasa_sr.c:16 */
+
+const int FREESASA_DEF_NUMBER_THREADS = 2; /* the threaded default, src/freesasa.c:31-36 */
+const freesasa_parameters freesasa_default_parameters = {
+    FREESASA_DEF_ALGORITHM, FREESASA_DEF_PROBE_RADIUS, FREESASA_DEF_SR_N, FREESASA_DEF_LR_N, 2};
+
+static freesasa_verbosity verbosity = FREESASA_V_NORMAL;
+static FILE *errlog = NULL;
+static const char *prog = "freesasa";
+
+int freesasa_set_verbosity(freesasa_verbosity v)
+{
+    if (v == FREESASA_V_NORMAL || v == FREESASA_V_NOWARNINGS || v == FREESASA_V_SILENT || v == FREESASA_V_DEBUG) {
+        verbosity = v;
+        return FREESASA_SUCCESS;
+    }
+    return FREESASA_WARN;
+}
+freesasa_verbosity freesasa_get_verbosity(void) { return verbosity; }
+void freesasa_set_err_out(FILE *fp)
+{
+    assert(fp);
+    errlog = fp;
+}
+FILE *freesasa_get_err_out(void) { return errlog; }
+
+static int report(int code, const char *where, int line, const char *fmt, ...)
+{
+    va_list ap;
+    FILE *fp = errlog ? errlog : stderr;
+    if (verbosity == FREESASA_V_SILENT) return code;
+    if (code == FREESASA_WARN && verbosity == FREESASA_V_NOWARNINGS) return code;
+    if (where)
+        fprintf(fp, "%s:%s:%d: %s: ", prog, where, line, code == FREESASA_WARN ? "warning" : "error");
+    else
+        fprintf(fp, "%s: %s: ", prog, code == FREESASA_WARN ? "warning" : "error");
+    va_start(ap, fmt);
+    vfprintf(fp, fmt, ap);
+    va_end(ap);
+    fputc('\n', fp);
+    fflush(fp);
+    return code;
+}
+#define FAIL_MSG(...) report(FREESASA_FAIL, __FILE__, __LINE__, __VA_ARGS__)
+#define WARN_MSG(...) report(FREESASA_WARN, NULL, 0, __VA_ARGS__)
+
+/* shared validation of src/sasa_lr.c:169-193 / src/sasa_sr.c:173-200; returns 1 if the caller should
+ * return *rc immediately */
+static int validate(const char *alg, const char *func, int n_atoms, int n_threads, int resolution, int *rc)
+{
+    *rc = FREESASA_SUCCESS;
+    if (n_threads > MAX_THREADS) {
+        *rc = FAIL_MSG("%s does not support more than %d threads", alg, MAX_THREADS);
+        return 1;
+    }
+    if (resolution <= 0) {
+        *rc = FAIL_MSG("%d is an invalid resolution in %s, must be > 0", resolution, alg);
+        return 1;
+    }
+    if (n_atoms == 0) {
+        *rc = WARN_MSG("in %s(): empty coordinates", func);
+        return 1;
+    }
+    if (n_threads > n_atoms)
+        WARN_MSG("no sense in having more threads than atoms, only using %d threads", n_atoms);
+    return 0;
+}
+
+int freesasa_lee_richards(double *sasa, const coord_t *c, const double *radii, const freesasa_parameters *param)
+{
+    int rc;
+    assert(sasa);
+    assert(c);
+    assert(radii);
+    if (param == NULL) param = &freesasa_default_parameters;
+    if (validate("L&R", __func__, c->n, param->n_threads, param->lee_richards_n_slices, &rc)) return rc;
+    if (fsb200_lr(sasa, c->xyz, radii, c->n, param->probe_radius, param->lee_richards_n_slices) != FSB200_SUCCESS)
+        return FAIL_MSG("B200 engine: %s", fsb200_last_error());
+    return FREESASA_SUCCESS;
+}
+
+int freesasa_shrake_rupley(double *sasa, const coord_t *c, const double *radii, const freesasa_parameters *param)
+{
+    int rc;
+    assert(sasa);
+    assert(c);
+    assert(radii);
+    if (param == NULL) param = &freesasa_default_parameters;
+    if (validate("S&R", __func__, c->n, param->n_threads, param->shrake_rupley_n_points, &rc)) return rc;
+    if (fsb200_sr(sasa, c->xyz, radii, c->n, param->probe_radius, param->shrake_rupley_n_points) != FSB200_SUCCESS)
+        return FAIL_MSG("B200 engine: %s", fsb200_last_error());
+    return FREESASA_SUCCESS;
+}
+
+static freesasa_result *result_new(int n)
+{
+    freesasa_result *r = malloc(sizeof *r);
+    if (r == NULL) {
+        FAIL_MSG("Out of memory");
+        return NULL;
+    }
+    r->sasa = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (r->sasa == NULL) {
+        FAIL_MSG("Out of memory");
+        free(r);
+        return NULL;
+    }
+    r->n_atoms = n;
+    r->total = 0;
+    return r;
+}
+
+void freesasa_result_free(freesasa_result *r)
+{
+    if (r) {
+        free(r->sasa);
+        free(r);
+    }
+}
+
+static void finish_result(freesasa_result *r, const freesasa_parameters *p)
+{
+    int i;
+    r->total = 0; /* serial sum in atom order, as src/freesasa.c:113-116 */
+    for (i = 0; i < r->n_atoms; ++i) r->total += r->sasa[i];
+    r->parameters = *p;
+}
+
+freesasa_result *freesasa_calc(const coord_t *c, const double *radii, const freesasa_parameters *parameters)
+{
+    freesasa_result *result;
+    int ret = FREESASA_SUCCESS;
+    assert(c);
+    assert(radii);
+    result = result_new(c->n);
+    if (result == NULL) {
+        FAIL_MSG("");
+        return NULL;
+    }
+    if (parameters == NULL) parameters = &freesasa_default_parameters;
+    switch (parameters->alg) {
+    case FREESASA_SHRAKE_RUPLEY:
+        ret = freesasa_shrake_rupley(result->sasa, c, radii, parameters);
+        break;
+    case FREESASA_LEE_RICHARDS:
+        ret = freesasa_lee_richards(result->sasa, c, radii, parameters);
+        break;
+    default:
+        assert(0);
+        break;
+    }
+    if (ret == FREESASA_FAIL) {
+        freesasa_result_free(result);
+        return NULL;
+    }
+    finish_result(result, parameters);
+    return result;
+}
+
+freesasa_result *freesasa_calc_coord(const double *xyz, const double *radii, int n, const freesasa_parameters *parameters)
+{
+    coord_t view; /* linked view of the caller's array: zero-copy, read-only (src/coord.c:72-88) */
+    freesasa_result *result;
+    assert(xyz);
+    assert(radii);
+    assert(n > 0);
+    view.n = n;
+    view.is_linked = 1;
+    view.xyz = (double *)xyz;
+    result = freesasa_calc(&view, radii, parameters);
+    if (result == NULL) FAIL_MSG("");
+    return result;
+}
+
+int freesasa_calc_coord_batch(int n_struct, const double *const *xyz, const double *const *radii, const int *n_atoms,
+                              const freesasa_parameters *parameters, freesasa_result **results)
+{
+    int k, rc, resolution;
+    double **sasa;
+    if (parameters == NULL) parameters = &freesasa_default_parameters;
+    if (n_struct <= 0 || !xyz || !radii || !n_atoms || !results) return FAIL_MSG("invalid batch arguments");
+    resolution = parameters->alg == FREESASA_LEE_RICHARDS ? parameters->lee_richards_n_slices
+                                                          : parameters->shrake_rupley_n_points;
+    for (k = 0; k < n_struct; ++k) {
+        results[k] = NULL;
+        if (n_atoms[k] <= 0) return FAIL_MSG("structure %d has no atoms", k);
+        if (validate(parameters->alg == FREESASA_LEE_RICHARDS ? "L&R" : "S&R", __func__, n_atoms[k],
+                     k == 0 ? parameters->n_threads : 1, resolution, &rc))
+            return rc == FREESASA_WARN ? FREESASA_FAIL : rc;
+    }
+    sasa = malloc(sizeof(double *) * (size_t)n_struct);
+    if (!sasa) return FAIL_MSG("Out of memory");
+    for (k = 0; k < n_struct; ++k) {
+        results[k] = result_new(n_atoms[k]);
+        if (!results[k]) goto cleanup;
+        sasa[k] = results[k]->sasa;
+    }
+    if (fsb200_calc_batch((int)parameters->alg, n_struct, n_atoms, xyz, radii, sasa, parameters->probe_radius,
+                          resolution) != FSB200_SUCCESS) {
+        FAIL_MSG("B200 engine: %s", fsb200_last_error());
+        goto cleanup;
+    }
+    for (k = 0; k < n_struct; ++k) finish_result(results[k], parameters);
+    free(sasa);
+    return FREESASA_SUCCESS;
+cleanup:
+    for (k = 0; k < n_struct; ++k) {
+        freesasa_result_free(results[k]);
+        results[k] = NULL;
+    }
+    free(sasa);
+    return FREESASA_FAIL;
+}

@@ -1,0 +1,542 @@
+// freesasa_b200/csrc/integrate.cu — the two surface integrators as persistent sm_100a kernels.
+//
+// One CTA = 8 warps; one work item = up to 8 atoms of one grid cell, one warp per atom.
+// Per item the 27-cell neighbourhood (9 contiguous runs of the cell-sorted atom array, because x
+// is the fastest cell coordinate) is staged into shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier, SASS UBLKCP).  Each warp then
+//   1. filters the staged candidates with the reference's exact fp64 contact test
+//      dx*dx+dy*dy+dz*dz < (Ri+Rj)^2 (src/nb.c:483-491) and ballot-compacts the hits into its
+//      private shared-memory list, expressed in the atom-local frame (differences formed in fp64,
+//      then rounded) — the neighbour SET is therefore identical to the reference's, without its
+//      ~10 % duplicate entries (forward-cell rule, src/nb.c:103-110) and without any global
+//      adjacency array;
+//   2. Lee & Richards (src/sasa_lr.c:270-408): lanes = neighbours.  Per slice every lane derives
+//      its neighbour's buried arc [beta-alpha, beta+alpha]; arcs are ballot-compacted to shared
+//      memory and merged without sorting:  exposed = sum_k max(0, s_k - max(W, P_k)) +
+//      max(0, 2pi - max_k e_k), P_k = max{e_m : (s_m,m) < (s_k,k)}, W = wrapped coverage.
+//      beta = atan2(dy,dx)+pi is slice-invariant and hoisted out of the slice loop (the reference
+//      recomputes it per slice, src/sasa_lr.c:337).  alpha uses the cancellation-free half-angle
+//      form tan^2(alpha/2) = (a+b-d)(d+b-a) / ((d+a-b)(a+b+d)) instead of acos of a quotient.
+//   3. Shrake & Rupley (src/sasa_sr.c:276-338): lanes = test points.  Point u of atom i is hidden
+//      by neighbour a iff u.D_a >= t_a with D_a = x_a - x_i, t_a = (Ri^2+|D_a|^2-Ra^2)/(2Ri)
+//      (algebraically the reference's |Ri u + x_i - x_a|^2 <= Ra^2): 3 FMA + compare per test in
+//      fp32; results inside a rounding band are re-decided by replaying the reference's exact
+//      fp64 expression, so every inside/outside decision equals the reference's.
+#include "engine.cuh"
+
+namespace fsb200 {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- PTX wrappers: mbarrier + TMA bulk copy ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    const uint32_t addr = smem_addr(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA, 1-D); bytes must be a multiple of 16, both addresses 16-B aligned
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ---- per-warp record types ------------------------------------------------------------------------
+template <typename T> struct alignas(4 * sizeof(T)) Rec4 { T a, b, c, d; };   // raw {dx,dy,dz,R}; LR {dz,R,dxy,beta}; SR {dx,dy,dz,t}
+template <typename T> struct alignas(2 * sizeof(T)) Arc { T st, en; };
+
+template <typename T> struct Consts;
+template <> struct Consts<float> {
+    static __device__ __forceinline__ float two_pi() { return 6.283185307179586f; }
+    static __device__ __forceinline__ float pi() { return 3.141592653589793f; }
+};
+template <> struct Consts<double> {
+    static __device__ __forceinline__ double two_pi() { return 6.283185307179586; }
+    static __device__ __forceinline__ double pi() { return 3.141592653589793; }
+};
+
+template <int ALG, typename T> struct WarpLayout {
+    // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries
+    static __host__ __device__ constexpr size_t bytes(int cap)
+    {
+        return (size_t)cap * (sizeof(Rec4<T>) + (ALG == 0 ? sizeof(Arc<T>) : sizeof(int)));
+    }
+};
+
+struct Self {
+    double x, y, z, R;
+};
+
+// ---- step 1: neighbour gather ------------------------------------------------------------------
+// Appends every candidate of base[0..cnt) that touches `self` to recs, in the atom-local frame
+// (differences formed in fp64, then rounded to T):
+//   ALG 0 (L&R): raw {dx, dy, dz, Rj}, turned into {dz, Rj, dxy, beta} by lr_prepare()
+//   ALG 1 (S&R): {dx, dy, dz, t_j}, t_j = (Ri^2 + |D|^2 - Rj^2) / (2 Ri) evaluated in fp64,
+//                plus the candidate's index (index_base + c) for the exact re-check
+// skip = index (within this run) of the atom itself, or -1.  Returns the new neighbour count;
+// entries beyond `cap` are counted but not stored.
+template <int ALG, typename T>
+__device__ __forceinline__ int gather_run(const double4 *base, int cnt, int skip, int index_base, const Self &s,
+                                          Rec4<T> *recs, int *cidx, int nn, int cap, int lane)
+{
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const int c = c0 + lane;
+        bool hit = false;
+        double dx = 0, dy = 0, dz = 0, Rj = 0, d2 = 0;
+        if (c < cnt && c != skip) {
+            const double4 q = base[c];
+            Rj = q.w;
+            // the reference's comparison, term for term and without FMA contraction (src/nb.c:483-491)
+            const double cut = __dadd_rn(s.R, Rj);
+            const double cut2 = __dmul_rn(cut, cut);
+            dx = __dsub_rn(q.x, s.x);
+            dy = __dsub_rn(q.y, s.y);
+            dz = __dsub_rn(q.z, s.z);
+            d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            hit = d2 < cut2;
+        }
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (hit) {
+            const int slot = nn + __popc(m & lanemask_lt());
+            if (slot < cap) {
+                Rec4<T> r;
+                r.a = (T)dx; r.b = (T)dy; r.c = (T)dz;
+                if (ALG == 0) {
+                    r.d = (T)Rj;
+                } else {
+                    r.d = s.R > 0.0 ? (T)((s.R * s.R + d2 - Rj * Rj) / (2.0 * s.R)) : (T)0;
+                    cidx[slot] = index_base + c;
+                }
+                recs[slot] = r;
+            }
+        }
+        nn += __popc(m);
+    }
+    return nn;
+}
+
+// ---- step 2: Lee & Richards ----------------------------------------------------------------------
+// raw {dx,dy,dz,R} -> {dz, R, dxy, beta}
+template <typename T>
+__device__ __forceinline__ void lr_prepare(Rec4<T> *recs, int nn, int lane)
+{
+    for (int j = lane; j < nn; j += 32) {
+        const Rec4<T> r = recs[j];
+        Rec4<T> o;
+        o.a = r.c;
+        o.b = r.d;
+        o.c = sqrt(r.a * r.a + r.b * r.b);                 // src/nb.c:440
+        o.d = atan2(r.b, r.a) + Consts<T>::pi();           // src/sasa_lr.c:337, hoisted
+        recs[j] = o;
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__device__ __forceinline__ double lr_atom(const Rec4<T> *recs, Arc<T> *arcs, int nn, double Ri_d, int ns, int lane)
+{
+    const T Ri = (T)Ri_d;
+    const T two_pi = Consts<T>::two_pi();
+    const double delta = 2.0 * Ri_d / ns;                  // src/sasa_lr.c:304
+    const unsigned lt = lanemask_lt();
+    double acc = 0.0;                                      // per-lane share of the exposed angle, all slices
+
+    for (int s = 0; s < ns; ++s) {
+        const T zr = (T)(-Ri_d + (s + 0.5) * delta);       // slice centre relative to the atom centre (:305-307)
+        const T az = fabs(zr);
+        const T a2 = (Ri - az) * (Ri + az);                // Ri'^2 (:309), factored to avoid cancellation
+        if (!(a2 > (T)0)) continue;                        // :310-312
+        const T a = sqrt(a2);
+        int narc = 0;
+        bool buried = false;
+        for (int base = 0; base < nn; base += 32) {
+            const int j = base + lane;
+            bool has = false, bur = false;
+            T st = 0, en = 0;
+            if (j < nn) {
+                const Rec4<T> r = recs[j];                 // {dz, R, dxy, beta}
+                const T dj = fabs(r.a - zr);               // :317
+                if (dj < r.b) {                            // :320
+                    const T b = sqrt((r.b - dj) * (r.b + dj));  // Rj' (:321-322)
+                    const T d = r.c;
+                    const T f1 = (a + b) - d;              // > 0  <=> circles touch      (:324)
+                    if (f1 > (T)0) {
+                        const T f3 = (d + a) - b;          // < 0  <=> circle i inside j  (:327)
+                        if (f3 < (T)0) {
+                            bur = true;
+                        } else {
+                            const T f2 = (d + b) - a;      // < 0  <=> circle j inside i  (:331)
+                            if (!(f2 < (T)0)) {
+                                // alpha = acos((a^2+d^2-b^2)/(2ad)) (:335) in half-angle form
+                                const T alpha = (T)2 * atan2(sqrt(f1 * f2), sqrt(f3 * ((a + b) + d)));
+                                st = r.d - alpha;          // :338-341, kept as [st, st+2alpha) with st in [0,2pi)
+                                if (st < (T)0) st += two_pi;
+                                en = st + (T)2 * alpha;
+                                has = true;
+                            }
+                        }
+                    }
+                }
+            }
+            if (__any_sync(kFull, bur)) { buried = true; break; }
+            const unsigned m = __ballot_sync(kFull, has);
+            if (has) {
+                Arc<T> arc;
+                arc.st = st; arc.en = en;
+                arcs[narc + __popc(m & lt)] = arc;
+            }
+            narc += __popc(m);
+        }
+        if (buried) continue;                              // :359
+        if (narc == 0) {                                   // :395
+            if (lane == 0) acc += (double)two_pi;
+            continue;
+        }
+        __syncwarp();
+        // sort-free union of arcs on the circle (equivalent to :367-408)
+        T max_en = 0;
+        for (int k = lane; k < narc; k += 32) {
+            const Arc<T> me = arcs[k];
+            T P = 0, mx = 0;
+            for (int m = 0; m < narc; ++m) {
+                const Arc<T> o = arcs[m];                  // warp-uniform address: shared-memory broadcast
+                mx = fmax(mx, o.en);
+                if (o.st < me.st || (o.st == me.st && m < k)) P = fmax(P, o.en);
+            }
+            const T W = fmax(mx - two_pi, (T)0);           // part of [0, .) covered by arcs that wrap past 2pi
+            acc += (double)fmax(me.st - fmax(W, P), (T)0);
+            max_en = mx;
+        }
+        if (lane == 0) acc += (double)fmax(two_pi - max_en, (T)0);
+        __syncwarp();
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    return delta * Ri_d * acc;                             // :360: delta * R_i * exposed angle
+}
+
+// ---- step 3: Shrake & Rupley ---------------------------------------------------------------------
+// fp32 decision band of this atom: the dot product and t each carry at most ~4e-7 * (|D|+|t|) of
+// rounding; every test closer than 10x that to the threshold is re-decided exactly in fp64.
+template <typename T>
+__device__ __forceinline__ float sr_band(const Rec4<T> *recs, int nn, int lane)
+{
+    float scale = 0.f;
+    for (int j = lane; j < nn; j += 32) {
+        const Rec4<T> r = recs[j];
+        const float dx = (float)r.a, dy = (float)r.b, dz = (float)r.c;
+        scale = fmaxf(scale, sqrtf(dx * dx + dy * dy + dz * dz) + fabsf((float)r.d));
+    }
+    for (int o = 16; o; o >>= 1) scale = fmaxf(scale, __shfl_xor_sync(kFull, scale, o));
+    return 4e-6f * scale + 1e-30f;
+}
+
+// the reference's own expression for "test point q of self is inside neighbour cand"
+// (src/sasa_sr.c:297-299 scale+translate via src/coord.c:306-342, then :312-317), no FMA contraction
+__device__ __forceinline__ bool sr_exact_hidden(const double *pd, int q, const Self &s, const double4 cand)
+{
+    const double px = __dadd_rn(__dmul_rn(pd[3 * q], s.R), s.x);
+    const double py = __dadd_rn(__dmul_rn(pd[3 * q + 1], s.R), s.y);
+    const double pz = __dadd_rn(__dmul_rn(pd[3 * q + 2], s.R), s.z);
+    const double dx = __dsub_rn(px, cand.x), dy = __dsub_rn(py, cand.y), dz = __dsub_rn(pz, cand.z);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double r2 = __dmul_rn(cand.w, cand.w);           // src/sasa_sr.c:146
+    return !(d2 > r2);
+}
+
+template <typename T>
+__device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, const double4 *cand_base, int nn,
+                                          const Self &s, int npts, const float4 *pf, const double *pd, int lane)
+{
+    int exposed = 0;
+    if (sizeof(T) == 8) {  // fp64 mode: the reference's expression for every pair
+        for (int q0 = 0; q0 < npts; q0 += 32) {
+            const int q = q0 + lane;
+            bool bur = q >= npts;
+            for (int k = 0; k < nn; ++k) {
+                if (!bur) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[k]]);
+                if (__all_sync(kFull, bur)) break;
+            }
+            exposed += __popc(__ballot_sync(kFull, !bur));
+        }
+    } else {
+        const float band = sr_band<T>(recs, nn, lane);
+        for (int q0 = 0; q0 < npts; q0 += 32) {
+            const int q = q0 + lane;
+            const bool active = q < npts;
+            const float4 u = active ? pf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            bool bur = !active;
+            for (int k = 0; k < nn; ++k) {
+                const Rec4<T> r = recs[k];                 // warp-uniform address: shared-memory broadcast
+                const float diff = fmaf(u.x, (float)r.a, fmaf(u.y, (float)r.b, u.z * (float)r.c)) - (float)r.d;
+                if (diff > band) bur = true;
+                else if (diff >= -band && !bur) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[k]]);
+                if (__all_sync(kFull, bur)) break;
+            }
+            exposed += __popc(__ballot_sync(kFull, !bur));
+        }
+    }
+    // src/sasa_sr.c:337, same expression order
+    return (4.0 * 3.14159265358979323846 * s.R * s.R * exposed) / npts;
+}
+
+// ---- one atom after its neighbours have been gathered ------------------------------------------------
+template <int ALG, typename T> struct WarpMem {
+    Rec4<T> *recs;
+    Arc<T> *arcs;   // L&R only
+    int *cidx;      // S&R only
+    __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
+    {
+        recs = reinterpret_cast<Rec4<T> *>(mem);
+        arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
+    }
+};
+
+template <int ALG, typename T>
+__device__ __forceinline__ void finish_atom(const Workspace &ws, const IntegrateArgs &args, const WarpMem<ALG, T> &wm,
+                                            const double4 *cand_base, const Self &s, int nn, int cap, int pos,
+                                            bool allow_overflow, int lane)
+{
+    __syncwarp();
+    if (nn > cap) {
+        if (allow_overflow && lane == 0) {
+            ws.overflow[atomicAdd(ws.counters + kCtrOverflow, 1)] = pos;
+            atomicMax(ws.counters + kCtrMaxCand, nn);
+        }
+        return;
+    }
+    double area = 0.0;
+    if (s.R > 0.0) {
+        if (ALG == 0) {
+            lr_prepare<T>(wm.recs, nn, lane);
+            area = lr_atom<T>(wm.recs, wm.arcs, nn, s.R, args.resolution, lane);
+        } else {
+            area = sr_atom<T>(wm.recs, wm.cidx, cand_base, nn, s, args.resolution, args.points_f, args.points_d, lane);
+        }
+    }
+    if (lane == 0) {
+        const int i = ws.perm[pos];
+        args.out[args.sorted_output ? pos : i] = area;
+        if (args.nn_out) args.nn_out[i] = nn;
+    }
+}
+
+__device__ __forceinline__ Self load_self(const double4 me)
+{
+    Self s;
+    s.x = me.x; s.y = me.y; s.z = me.z; s.R = me.w;
+    return s;
+}
+
+// 9 runs of the sorted atom array covering the 27 cells around `cell` (local id) of structure g
+__device__ __forceinline__ void cell_run(const Workspace &ws, const GridDesc &g, int cx, int cy, int cz, int r,
+                                         int *begin, int *count)
+{
+    const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+    *begin = 0;
+    *count = 0;
+    if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) return;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    const int row = g.cell_base + g.dim[0] * (y + g.dim[1] * z);
+    const int b = ws.cell_start[row + x0], e = ws.cell_start[row + x1 + 1];
+    *begin = b;
+    *count = e - b;
+}
+
+template <int ALG, typename T>
+__global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, IntegrateArgs args)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double4 *tile = reinterpret_cast<double4 *>(smem);
+    __shared__ uint64_t bar;
+    __shared__ int s_item;
+    __shared__ int s_begin[9], s_count[9];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *warp_mem = smem + (size_t)kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
+    const int n_items = ws.counters[kCtrItems];
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(ws.counters + kCtrQueue, 1);
+        __syncthreads();
+        const int item_idx = s_item;
+        if (item_idx >= n_items) break;
+        const Item it = ws.items[item_idx];
+        const bool mine = it.first < args.shard_end && it.first + it.count > args.shard_begin;
+        if (mine) {
+            const GridDesc &g = ws.grid[it.sid];
+            const int cx = it.cell % g.dim[0], cy = (it.cell / g.dim[0]) % g.dim[1], cz = it.cell / (g.dim[0] * g.dim[1]);
+            if (tid < 9) cell_run(ws, g, cx, cy, cz, tid, &s_begin[tid], &s_count[tid]);
+            __syncthreads();
+            int off[10];
+            off[0] = 0;
+            for (int r = 0; r < 9; ++r) off[r + 1] = off[r] + s_count[r];
+            const int total = off[9];
+            const bool staged = total <= kTileCap;
+            const int pos = it.first + warp;
+            const bool active = warp < it.count && pos >= args.shard_begin && pos < args.shard_end;
+            const WarpMem<ALG, T> wm(warp_mem, kNbCap);
+            if (staged) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bar, (uint32_t)total * (uint32_t)sizeof(double4));
+                    for (int r = 0; r < 9; ++r)
+                        if (s_count[r] > 0)
+                            tma_load_1d(tile + off[r], ws.atoms + s_begin[r], (uint32_t)s_count[r] * (uint32_t)sizeof(double4), &bar);
+                }
+                mbar_wait(&bar, parity);
+                parity ^= 1;
+                if (active) {
+                    const int self_idx = off[4] + (pos - s_begin[4]);
+                    const Self s = load_self(tile[self_idx]);
+                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.recs, wm.cidx, 0, kNbCap, lane);
+                    finish_atom<ALG, T>(ws, args, wm, tile, s, nn, kNbCap, pos, true, lane);
+                }
+            } else if (active) {  // oversized neighbourhood: read the candidates straight from global memory
+                const Self s = load_self(ws.atoms[pos]);
+                int nn = 0;
+                for (int r = 0; r < 9; ++r)
+                    nn = gather_run<ALG, T>(ws.atoms + s_begin[r], s_count[r], r == 4 ? pos - s_begin[4] : -1, s_begin[r], s,
+                                            wm.recs, wm.cidx, nn, kNbCap, lane);
+                finish_atom<ALG, T>(ws, args, wm, ws.atoms, s, nn, kNbCap, pos, true, lane);
+            }
+        }
+        __syncthreads();  // tile, s_item and s_begin/s_count are reused by the next item
+    }
+}
+
+// Atoms whose neighbour list exceeded kNbCap: one warp per atom, lists in global scratch.
+template <int ALG, typename T>
+__global__ void __launch_bounds__(128) k_overflow(Workspace ws, IntegrateArgs args, int n_overflow, int list_cap,
+                                                  unsigned char *scratch)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned char *warp_mem = scratch + (size_t)gwarp * WarpLayout<ALG, T>::bytes(list_cap);
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(ws.counters + kCtrQueue2, 1);
+        k = __shfl_sync(kFull, k, 0);
+        if (k >= n_overflow) break;
+        const int pos = ws.overflow[k];
+        const int i = ws.perm[pos];
+        const int sid = ws.n_struct == 1 ? 0 : find_structure(ws.offsets, ws.n_struct, i);
+        const GridDesc &g = ws.grid[sid];
+        const double4 me = ws.atoms[pos];
+        int c[3];
+        cell_coords(g, me.x, me.y, me.z, c);
+        const Self s = load_self(me);
+        const WarpMem<ALG, T> wm(warp_mem, list_cap);
+        int nn = 0;
+        for (int r = 0; r < 9; ++r) {
+            int b, n;
+            cell_run(ws, g, c[0], c[1], c[2], r, &b, &n);
+            nn = gather_run<ALG, T>(ws.atoms + b, n, r == 4 ? pos - b : -1, b, s, wm.recs, wm.cidx, nn, list_cap, lane);
+        }
+        finish_atom<ALG, T>(ws, args, wm, ws.atoms, s, nn, list_cap, pos, false, lane);
+        __syncwarp();
+    }
+}
+
+template <int ALG, typename T> size_t cta_smem_bytes()
+{
+    return (size_t)kTileCap * sizeof(double4) + (size_t)kWarpsPerCta * WarpLayout<ALG, T>::bytes(kNbCap);
+}
+
+template <int ALG, typename T> int configure_and_occupancy(int device)
+{
+    const size_t smem = cta_smem_bytes<ALG, T>();
+    cudaFuncSetAttribute(k_integrate<ALG, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate<ALG, T>, kCtaThreads, smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}
+
+}  // namespace
+
+int integrate_grid_ctas(int alg, int precision, int device)
+{
+    if (alg == 0) return precision == 0 ? configure_and_occupancy<0, float>(device) : configure_and_occupancy<0, double>(device);
+    return precision == 0 ? configure_and_occupancy<1, float>(device) : configure_and_occupancy<1, double>(device);
+}
+
+int launch_integrate(const Workspace &ws, const IntegrateArgs &args, cudaStream_t stream)
+{
+    const int grid = args.grid_ctas;
+    if (args.alg == 0) {
+        if (args.precision == 0)
+            k_integrate<0, float><<<grid, kCtaThreads, cta_smem_bytes<0, float>(), stream>>>(ws, args);
+        else
+            k_integrate<0, double><<<grid, kCtaThreads, cta_smem_bytes<0, double>(), stream>>>(ws, args);
+    } else {
+        if (args.precision == 0)
+            k_integrate<1, float><<<grid, kCtaThreads, cta_smem_bytes<1, float>(), stream>>>(ws, args);
+        else
+            k_integrate<1, double><<<grid, kCtaThreads, cta_smem_bytes<1, double>(), stream>>>(ws, args);
+    }
+    return 1;
+}
+
+int overflow_warps(int n_overflow)
+{
+    const int want = n_overflow < 1 ? 1 : n_overflow;
+    return want < 1024 ? ((want + 3) / 4) * 4 : 1024;  // 4 warps per CTA
+}
+
+size_t overflow_scratch_bytes(int n_warps, int list_cap, int precision)
+{
+    // sized for the larger of the two algorithms so one buffer serves both
+    const size_t a = precision == 0 ? WarpLayout<0, float>::bytes(list_cap) : WarpLayout<0, double>::bytes(list_cap);
+    const size_t b = precision == 0 ? WarpLayout<1, float>::bytes(list_cap) : WarpLayout<1, double>::bytes(list_cap);
+    return (size_t)n_warps * (a > b ? a : b);
+}
+
+int launch_overflow(const Workspace &ws, const IntegrateArgs &args, int n_overflow, int list_cap, void *scratch,
+                    cudaStream_t stream)
+{
+    const int warps = overflow_warps(n_overflow);
+    const int grid = warps / 4;
+    unsigned char *sc = static_cast<unsigned char *>(scratch);
+    if (args.alg == 0) {
+        if (args.precision == 0) k_overflow<0, float><<<grid, 128, 0, stream>>>(ws, args, n_overflow, list_cap, sc);
+        else k_overflow<0, double><<<grid, 128, 0, stream>>>(ws, args, n_overflow, list_cap, sc);
+    } else {
+        if (args.precision == 0) k_overflow<1, float><<<grid, 128, 0, stream>>>(ws, args, n_overflow, list_cap, sc);
+        else k_overflow<1, double><<<grid, 128, 0, stream>>>(ws, args, n_overflow, list_cap, sc);
+    }
+    return 1;
+}
+
+}  // namespace fsb200

@@ -1,0 +1,107 @@
+"""CPU tests: the C-ABI libraries load and export every symbol the headers declare; host-side
+validation mirrors the reference (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import freesasa_b200 as fs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:fsb200|freesasa)_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+
+    g.build()
+    return fs.library_paths()
+
+
+def test_engine_exports_every_declared_symbol(built):
+    lib = ctypes.CDLL(built["engine"])
+    names = _declared("fsb200.h")
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_host_layer_exports_every_declared_symbol(built):
+    ctypes.CDLL(built["engine"], mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(built["host"])
+    for name in _declared("freesasa_b200_host.h"):
+        assert hasattr(lib, name), name
+    p = fs.Parameters.in_dll(lib, "freesasa_default_parameters")  # reference src/freesasa.c:38-43
+    assert (p.alg, p.probe_radius, p.shrake_rupley_n_points, p.lee_richards_n_slices, p.n_threads) == (0, 1.4, 100, 20, 2)
+
+
+def test_struct_layouts_match_reference_abi():
+    # reference src/freesasa.h:232-238,267-272 on LP64: 32-byte parameters, 56-byte result
+    assert ctypes.sizeof(fs.Parameters) == 32
+    assert fs.Parameters.probe_radius.offset == 8 and fs.Parameters.n_threads.offset == 24
+    from freesasa_b200 import _CResult
+
+    assert ctypes.sizeof(_CResult) == 56 and _CResult.parameters.offset == 24
+
+
+def test_shard_ranges_partition(built):
+    lib = ctypes.CDLL(built["engine"])
+    for n in (1, 7, 100000, 1000003):
+        for k in (1, 2, 3, 8):
+            edges = [(lib.fsb200_shard_begin(n, i, k), lib.fsb200_shard_end(n, i, k)) for i in range(k)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(k - 1))
+
+
+def test_parameter_validation_like_reference(built, capfd):
+    """reference src/sasa_lr.c:177-183, src/sasa_sr.c:188-193 and tests/test-cli.in:162-164,194-196:
+    more than 16 threads and non-positive resolutions are errors (NULL result) before any compute."""
+    H = fs._host_lib()
+    xyz = np.zeros(3)
+    rad = np.ones(1)
+    dp = ctypes.POINTER(ctypes.c_double)
+    for alg in (fs.LEE_RICHARDS, fs.SHRAKE_RUPLEY):
+        for bad in (fs.Parameters(alg, 1.4, 100, 20, 17), fs.Parameters(alg, 1.4, 0, 0, 1), fs.Parameters(alg, 1.4, -1, -1, 1)):
+            res = H.freesasa_calc_coord(xyz.ctypes.data_as(dp), rad.ctypes.data_as(dp), 1, ctypes.byref(bad))
+            assert not res
+    err = capfd.readouterr().err
+    assert "does not support more than 16 threads" in err
+    assert "invalid resolution" in err
+    H.freesasa_set_verbosity(2)  # FREESASA_V_SILENT
+    bad = fs.Parameters(0, 1.4, 100, 20, 17)
+    assert not H.freesasa_calc_coord(xyz.ctypes.data_as(dp), rad.ctypes.data_as(dp), 1, ctypes.byref(bad))
+    assert capfd.readouterr().err == ""
+    H.freesasa_set_verbosity(0)
+
+
+def test_no_cpu_fallback(built):
+    """Without a device every compute entry point must fail loudly, never fall back."""
+    if fs.available():
+        pytest.skip("a B200 is visible")
+    with pytest.raises(RuntimeError):
+        fs.Engine(0)
+    H = fs._host_lib()
+    H.freesasa_set_verbosity(2)
+    try:
+        with pytest.raises(RuntimeError, match="failed"):
+            fs.calc_coord(np.zeros((2, 3)), np.ones(2))
+    finally:
+        H.freesasa_set_verbosity(0)
+
+
+def test_product_never_touches_oracle():
+    """The product tree must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "freesasa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU", ""), os.path.join(dirpath, f)

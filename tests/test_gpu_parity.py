@@ -1,0 +1,257 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA engine, called through the C ABI /
+the reference-named C host layer, against the CPU oracle, the committed reference vectors and the
+reference's own known answers.
+
+Tolerances (north star): Lee-Richards per-atom |dSASA| <= 1e-3 Å^2 in the default fp32 mode (we
+assert 5e-4), <= 1e-8 in fp64 mode; Shrake-Rupley is a point count and must be EXACT (<= 1e-9 Å^2
+from the shared fp64 final multiply)."""
+import math
+
+import numpy as np
+import pytest
+
+import freesasa_b200 as fs
+from oracle import bindings as ob
+from tests import analytic
+
+pytestmark = pytest.mark.gpu
+
+LR_TOL_FP32 = 5e-4
+LR_TOL_FP64 = 1e-8
+SR_TOL = 1e-9
+PDBS = ["1ubq", "2jo4", "3bkr", "5dx9", "3bzd_trimmed", "1d3z"]
+
+
+@pytest.fixture(scope="module")
+def eng32():
+    e = fs.Engine(0, fs.FP32)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng64():
+    e = fs.Engine(0, fs.FP64)
+    yield e
+    e.close()
+
+
+def params(alg, res, threads=1, probe=1.4):
+    return fs.Parameters(alg, probe, res, res, threads)
+
+
+def maxerr(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max())
+
+
+# ---- reference golden totals through the reference-named entry point (tests/test_freesasa.c:155-178 ...) ----
+@pytest.mark.parametrize(
+    "name,alg,res,gold,tol",
+    [
+        ("1ubq", fs.LEE_RICHARDS, 20, 4804.055641, 2e-3),   # sum of 602 fp32-path areas
+        ("1ubq", fs.SHRAKE_RUPLEY, 100, 4834.716265, 1e-5),  # the reference's own tolerance
+        ("3bzd_trimmed", fs.SHRAKE_RUPLEY, 100, 16133.867124, 1e-5),
+        ("1d3z", fs.SHRAKE_RUPLEY, 100, 5000.340175, 1e-5),
+    ],
+)
+def test_published_totals(pdb_fixtures, name, alg, res, gold, tol):
+    r = fs.calc_coord(pdb_fixtures[name + "_xyz"], pdb_fixtures[name + "_radii"], params(alg, res))
+    assert abs(r.total - gold) < tol
+    assert r.n_atoms == len(pdb_fixtures[name + "_radii"])
+    assert abs(r.total - r.sasa.sum()) < 1e-9
+    assert r.parameters.alg == alg
+
+
+def test_thread_count_is_irrelevant(pdb_fixtures):  # tests/test_freesasa.c:404-429
+    x, r = pdb_fixtures["1ubq_xyz"], pdb_fixtures["1ubq_radii"]
+    a = fs.calc_coord(x, r, params(fs.SHRAKE_RUPLEY, 100, threads=1))
+    b = fs.calc_coord(x, r, params(fs.SHRAKE_RUPLEY, 100, threads=2))
+    np.testing.assert_array_equal(a.sasa, b.sasa)
+
+
+# ---- per-atom against committed vectors of the unmodified reference --------------------------------------
+@pytest.mark.parametrize("name", PDBS)
+def test_per_atom_pdb(pdb_fixtures, eng32, eng64, name):
+    x, r = pdb_fixtures[name + "_xyz"], pdb_fixtures[name + "_radii"]
+    assert maxerr(eng32.calc(fs.LEE_RICHARDS, x, r, 1.4, 20), pdb_fixtures[name + "_lr20"]) < LR_TOL_FP32
+    assert maxerr(eng64.calc(fs.LEE_RICHARDS, x, r, 1.4, 20), pdb_fixtures[name + "_lr20"]) < LR_TOL_FP64
+    assert maxerr(eng32.calc(fs.SHRAKE_RUPLEY, x, r, 1.4, 100), pdb_fixtures[name + "_sr100"]) < SR_TOL
+    assert maxerr(eng64.calc(fs.SHRAKE_RUPLEY, x, r, 1.4, 100), pdb_fixtures[name + "_sr100"]) < SR_TOL
+
+
+@pytest.mark.parametrize("key,alg,res", [("lr20", 0, 20), ("lr100", 0, 100), ("sr100", 1, 100), ("sr1000", 1, 1000)])
+def test_per_atom_synthetic(synthetic_fixtures, eng32, eng64, key, alg, res):
+    f = synthetic_fixtures
+    tol32, tol64 = (LR_TOL_FP32, LR_TOL_FP64) if alg == 0 else (SR_TOL, SR_TOL)
+    assert maxerr(eng32.calc(alg, f["g3000_xyz"], f["g3000_radii"], 1.4, res), f["g3000_" + key]) < tol32
+    assert maxerr(eng64.calc(alg, f["g3000_xyz"], f["g3000_radii"], 1.4, res), f["g3000_" + key]) < tol64
+
+
+def test_far_from_origin(synthetic_fixtures, eng32):
+    """PDB coordinates sit hundreds of Å from the origin; the local-frame fp32 path must not care."""
+    f = synthetic_fixtures
+    assert maxerr(eng32.calc(0, f["off1500_xyz"], f["off1500_radii"], 1.4, 20), f["off1500_lr20"]) < LR_TOL_FP32
+    assert maxerr(eng32.calc(1, f["off1500_xyz"], f["off1500_radii"], 1.4, 100), f["off1500_sr100"]) < SR_TOL
+    x = f["off1500_xyz"] + np.array([1.0e5, -2.0e5, 3.0e5])  # exactly representable shift
+    assert maxerr(eng32.calc(1, x, f["off1500_radii"], 1.4, 100), ob.oracle_calc(x, f["off1500_radii"], 1, 1.4, 100)) < SR_TOL
+
+
+# ---- neighbour search row (src/nb.c) ---------------------------------------------------------------------
+def test_neighbour_counts(eng32, synthetic_fixtures):
+    x, r = synthetic_fixtures["g3000_xyz"], synthetic_fixtures["g3000_radii"]
+    start, _ = ob.oracle_neighbours(x, r + 1.4)
+    np.testing.assert_array_equal(eng32.neighbour_counts(x, r, 1.4), np.diff(start))
+    v = np.array([0, 0, 0, 1, 1, 1, -1, 1, -1, 2, 0, -2, 2, 2, 0, -5, 5, 5], dtype=float)  # tests/test_nb.c:7-27
+    rr = np.array([4, 2, 2, 2, 2, 2], dtype=float)
+    start, _ = ob.oracle_neighbours(v, rr)
+    np.testing.assert_array_equal(eng32.neighbour_counts(v, rr, 0.0), np.diff(start))
+
+
+# ---- analytic known answers (tests/test_freesasa.c:27-43,59-136) -----------------------------------------
+@pytest.mark.parametrize("x1,x2", analytic.TWO_SPHERE_CASES)
+def test_two_spheres_analytic(x1, x2):
+    xyz, r = np.array([x1, x2], dtype=float), np.array([1.0, 2.0])
+    exact = analytic.surface_two_spheres(x1, x2, 1.0, 2.0, 1.4)
+    lr = fs.calc_coord(xyz, r, params(fs.LEE_RICHARDS, 20000)).total
+    sr = fs.calc_coord(xyz, r, params(fs.SHRAKE_RUPLEY, 5000)).total
+    assert analytic.rel_err(exact, lr) < 1e-5
+    assert analytic.rel_err(exact, sr) < 1e-3
+    assert abs(sr - ob.oracle_calc(xyz, r, 1, 1.4, 5000).sum()) < SR_TOL
+
+
+@pytest.mark.parametrize("alg,res,tol", [(0, 20000, 1e-5), (1, 5000, 1e-3)])
+def test_four_spheres_invariance(alg, res, tol):
+    r = np.array(analytic.FOUR_SPHERE_RADII)
+    ref = fs.calc_coord(np.array(analytic.FOUR_SPHERE_POSES[0], dtype=float), r, params(alg, res)).total
+    for pose in analytic.FOUR_SPHERE_POSES[1:]:
+        got = fs.calc_coord(np.array(pose, dtype=float), r, params(alg, res)).total
+        assert analytic.rel_err(ref, got) < tol
+
+
+def test_single_atom():  # tests/test_freesasa.c:138-153
+    for alg, res in [(0, 20), (1, 100)]:
+        r = fs.calc_coord(np.zeros((1, 3)), np.array([1.0]), params(alg, res))
+        assert abs(r.sasa[0] - r.total) < 1e-10
+        assert abs(r.total - 4 * math.pi * 2.4 * 2.4) < 1e-4
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------
+def test_edge_cases(eng32, eng64):
+    rng = np.random.default_rng(5)
+    cases = {
+        "two_isolated": (np.array([[0.0, 0, 0], [100.0, 0, 0]]), np.array([1.5, 2.0])),
+        "zero_radius_atoms": (rng.uniform(-8, 8, (300, 3)), rng.choice([0.0, 1.5, 1.9], 300)),
+        "buried_small_in_big": (np.array([[0.0, 0, 0], [0.3, 0.1, -0.2]]), np.array([5.0, 0.5])),
+        "line_along_z": (np.stack([np.zeros(40), np.zeros(40), np.arange(40) * 1.1], 1), np.full(40, 1.7)),
+        "flat_sheet": (np.concatenate([rng.uniform(-20, 20, (500, 2)), np.zeros((500, 1))], 1), np.full(500, 1.8)),
+        "wide_radii": (rng.uniform(-15, 15, (400, 3)), rng.uniform(0.5, 6.0, 400)),
+        "sparse_far_apart": (rng.uniform(-5000, 5000, (64, 3)), np.full(64, 1.8)),
+    }
+    for name, (x, r) in cases.items():
+        for alg, res, tol in [(0, 25, LR_TOL_FP32), (1, 173, SR_TOL)]:
+            want = ob.oracle_calc(x, r, alg, 1.4, res)
+            assert maxerr(eng32.calc(alg, x, r, 1.4, res), want) < tol, (name, alg)
+        assert maxerr(eng64.calc(0, x, r, 1.4, 25), ob.oracle_calc(x, r, 0, 1.4, 25)) < LR_TOL_FP64, name
+
+
+def test_zero_probe(eng32):
+    x, r = fs.workloads.globule(800, seed=3)
+    for alg, res, tol in [(0, 20, LR_TOL_FP32), (1, 100, SR_TOL)]:
+        assert maxerr(eng32.calc(alg, x, r, 0.0, res), ob.oracle_calc(x, r, alg, 0.0, res)) < tol
+
+
+def test_crowded_neighbourhoods_take_the_overflow_path(eng32, eng64):
+    """> 160 neighbours per atom (smem list capacity) and > 768 atoms per 27-cell tile."""
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-4.0, 4.0, (1500, 3))
+    r = rng.choice([1.2, 1.6, 1.9], 1500)
+    for alg, res, tol in [(0, 12, LR_TOL_FP32), (1, 96, SR_TOL)]:
+        got = eng32.calc(alg, x, r, 1.4, res)
+        st = eng32.stats()
+        assert st["n_overflow"] > 0 and st["max_neighbours"] > 160
+        assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
+    start, _ = ob.oracle_neighbours(x, r + 1.4)
+    np.testing.assert_array_equal(eng32.neighbour_counts(x, r, 1.4), np.diff(start))
+    assert maxerr(eng64.calc(0, x, r, 1.4, 12), ob.oracle_calc(x, r, 0, 1.4, 12)) < LR_TOL_FP64
+
+
+def test_duplicate_positions_do_not_poison(eng32):
+    """Coincident atoms make the reference's acos argument 0/0 (NaN area, src/sasa_lr.c:335); the engine
+    treats the coincident circle as a zero-length arc and must stay finite; S&R stays exact."""
+    x, r = fs.workloads.globule(400, seed=2)
+    x = np.concatenate([x, x[:5]])
+    r = np.concatenate([r, r[:5]])
+    lr = eng32.calc(0, x, r, 1.4, 20)
+    assert np.isfinite(lr).all()
+    assert maxerr(eng32.calc(1, x, r, 1.4, 100), ob.oracle_calc(x, r, 1, 1.4, 100)) < SR_TOL
+
+
+def test_non_finite_input_fails_loudly(eng32):
+    x, r = fs.workloads.globule(100, seed=1)
+    x[17, 1] = np.nan
+    with pytest.raises(RuntimeError, match="non-finite"):
+        eng32.calc(0, x, r, 1.4, 20)
+    x[17, 1] = 0.0
+    assert np.isfinite(eng32.calc(0, x, r, 1.4, 20)).all()  # context still usable
+
+
+def test_run_to_run_bit_identical(eng32):
+    x, r = fs.workloads.globule(5000, seed=4, shuffle=True)
+    a, b = eng32.calc(0, x, r, 1.4, 50), eng32.calc(0, x, r, 1.4, 50)
+    np.testing.assert_array_equal(a, b)
+    c, d = eng32.calc(1, x, r, 1.4, 200), eng32.calc(1, x, r, 1.4, 200)
+    np.testing.assert_array_equal(c, d)
+
+
+def test_shuffled_input_order(eng32):
+    x, r = fs.workloads.globule(4000, seed=6)
+    p = np.random.default_rng(0).permutation(4000)
+    a = eng32.calc(1, x, r, 1.4, 100)
+    b = eng32.calc(1, x[p], r[p], 1.4, 100)
+    np.testing.assert_array_equal(a[p], b)
+
+
+# ---- batches of independent structures (config C4 shape) -------------------------------------------------
+def test_batch_equals_individual(eng32):
+    structs = fs.workloads.batch(12, 300, 900, seed=1)
+    for alg, res, tol in [(0, 50, LR_TOL_FP32), (1, 100, SR_TOL)]:
+        outs = eng32.calc_batch(alg, structs, 1.4, res)
+        for (x, r), got in zip(structs, outs):
+            assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
+            np.testing.assert_array_equal(got, eng32.calc(alg, x, r, 1.4, res))
+    res = fs.calc_coord_batch(structs, params(fs.LEE_RICHARDS, 50))
+    assert len(res) == 12 and all(abs(a.total - a.sasa.sum()) < 1e-9 for a in res)
+
+
+# ---- device-resident path + sharding of one structure (config C5 shape) -----------------------------------
+def test_device_path_and_sharding(eng32):
+    import torch
+
+    x, r = fs.workloads.capsid(30000, r_out=60.0, seed=1)
+    dx = torch.tensor(x, device="cuda:0")
+    dr = torch.tensor(r, device="cuda:0")
+    whole = eng32.calc_device(0, dx, dr, 1.4, 30).cpu().numpy()
+    assert maxerr(whole, ob.oracle_calc(x, r, 0, 1.4, 30)) < LR_TOL_FP32
+    n, k = len(r), 4
+    gathered = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+    for i in range(k):
+        part = eng32.calc_device(0, dx, dr, 1.4, 30, shard=(i, k))
+        b, e = eng32.shard_range(n, i, k)
+        gathered[b:e] = part[b:e]
+    out = eng32.unpermute(gathered).cpu().numpy()
+    np.testing.assert_array_equal(out, whole)
+
+
+# ---- full-size benchmark configurations (C2, C3) ------------------------------------------------------------
+def test_full_size_100k(eng32, totals):
+    x, r = fs.workloads.globule(100000)
+    lr = eng32.calc(0, x, r, 1.4, 100)
+    want = ob.oracle_calc(x, r, 0, 1.4, 100)
+    assert maxerr(lr, want) < 1e-3  # the north-star tolerance at the headline configuration
+    assert abs(want.sum() - totals["measured"]["globule100k"]["lr100"]) < 1e-6
+    sr = eng32.calc(1, x, r, 1.4, 1000)
+    want_sr = ob.oracle_calc(x, r, 1, 1.4, 1000)
+    assert maxerr(sr, want_sr) < SR_TOL
+    assert abs(want_sr.sum() - totals["measured"]["globule100k"]["sr1000"]) < 1e-6
+    # size-independent properties: isolated far copy changes nothing; total bounded by sum of spheres
+    assert (lr >= 0).all() and (lr <= 4 * math.pi * (r + 1.4) ** 2 + 1e-6).all()
