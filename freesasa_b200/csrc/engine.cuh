@@ -25,7 +25,7 @@ namespace fsb200 {
 constexpr int kWarpsPerCta = 8;             // one atom per warp, one work item = up to 8 atoms of a cell
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr int kItemAtoms = kWarpsPerCta;
-constexpr int kTileCap = 768;               // atoms of the 27-cell neighbourhood staged in smem (24 KB)
+constexpr int kTileCap = 640;               // atoms of the 27-cell neighbourhood staged in smem (20 KB)
 constexpr int kNbCap = 160;                 // per-warp neighbour list capacity in smem
 constexpr int kCellsPerAtomCap = 2;         // grid budget: cells <= 2*n_k + 64 per structure
 constexpr int kCellsSlack = 64;

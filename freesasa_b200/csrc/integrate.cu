@@ -84,10 +84,12 @@ template <> struct Consts<double> {
 };
 
 template <int ALG, typename T> struct WarpLayout {
-    // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries
+    // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
+    //   L&R: records + arcs (cap + 4 sentinel slots) + exact arc starts;  S&R: records + candidate indices
     static __host__ __device__ constexpr size_t bytes(int cap)
     {
-        return (size_t)cap * (sizeof(Rec4<T>) + (ALG == 0 ? sizeof(Arc<T>) : sizeof(int)));
+        return ALG == 0 ? (size_t)cap * (sizeof(Rec4<T>) + sizeof(Arc<T>) + sizeof(T)) + 4 * sizeof(Arc<T>)
+                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
     }
 };
 
@@ -242,6 +244,147 @@ __device__ __forceinline__ double lr_atom(const Rec4<T> *recs, Arc<T> *arcs, int
     return delta * Ri_d * acc;                             // :360: delta * R_i * exposed angle
 }
 
+
+// ---- step 2b: the fp32 production path of Lee & Richards -------------------------------------------
+// Same mathematics as lr_atom<float>, with the two instruction hogs of that version (ncu, round 1:
+// atan2f + IEEE sqrtf = 40 % of all issued instructions, the tie-breaking all-pairs merge 33 %)
+// replaced:
+//   * alpha = 2 atan(sqrt(q)) with q = min(N,D)/max(N,D) in [0,1], N = f1 f2, D = f3 (a+b+d), via
+//     MUFU rcp/sqrt and a degree-7 minimax polynomial in q (|err| < 1.5e-7 rad), reflected for N > D;
+//   * every arc gets a UNIQUE integer sort key = (bits(start) & ~0xff) | arc index, so "arc m comes
+//     before arc k" is one integer compare; two starts within 256 ulp (6e-5 rad) may swap order,
+//     which changes the union only by that sliver and only in the ~1e-3 of slices where it happens.
+//     The exact start (kept in a side array) is still what the exposed gap is measured from.
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// atan(sqrt(q)) for q in [0,1]
+__device__ __forceinline__ float atan_sqrt01(float q)
+{
+    float p = -4.054468951e-03f;
+    p = fmaf(p, q, 2.186259337e-02f);
+    p = fmaf(p, q, -5.591178698e-02f);
+    p = fmaf(p, q, 9.642156725e-02f);
+    p = fmaf(p, q, -1.390861325e-01f);
+    p = fmaf(p, q, 1.994656231e-01f);
+    p = fmaf(p, q, -3.332986048e-01f);
+    p = fmaf(p, q, 9.999993355e-01f);
+    return fast_sqrt(q) * p;
+}
+
+struct alignas(8) KeyArc {
+    int key;    // order-preserving bits of the arc start with the low 8 bits replaced by the arc index
+    float en;   // start + 2 alpha (may exceed 2 pi: the arc wraps)
+};
+
+__device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
+                                               double Ri_d, int ns, int lane)
+{
+    const float Ri = (float)Ri_d;
+    const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+    const double delta = 2.0 * Ri_d / ns;
+    const unsigned lt = lanemask_lt();
+    double acc = 0.0;
+
+    for (int s = 0; s < ns; ++s) {
+        const float zr = (float)(-Ri_d + (s + 0.5) * delta);
+        const float az = fabsf(zr);
+        const float a2 = (Ri - az) * (Ri + az);
+        if (!(a2 > 0.f)) continue;
+        const float a = sqrtf(a2);                         // once per slice: keep the IEEE root
+        int narc = 0;
+        bool buried = false;
+        float my_max = 0.f;
+        for (int base = 0; base < nn; base += 32) {
+            const int j = base + lane;
+            bool has = false, bur = false;
+            float st = 0.f, en = 0.f;
+            if (j < nn) {
+                const Rec4<float> r = recs[j];             // {dz, R, dxy, beta}
+                const float dj = fabsf(r.a - zr);
+                if (dj < r.b) {
+                    const float b = fast_sqrt((r.b - dj) * (r.b + dj));
+                    const float d = r.c;
+                    const float ab = a + b;
+                    const float f1 = ab - d;
+                    if (f1 > 0.f) {
+                        const float f3 = (d + a) - b;
+                        if (f3 < 0.f) {
+                            bur = true;
+                        } else {
+                            const float f2 = (d + b) - a;
+                            if (!(f2 < 0.f)) {
+                                const float N = f1 * f2, D = f3 * (ab + d);
+                                const float hi = fmaxf(N, D), lo = fminf(N, D);
+                                const float q = hi > 0.f ? lo * fast_rcp(hi) : 0.f;
+                                const float u2 = 2.f * atan_sqrt01(fminf(q, 1.f));
+                                const float alpha = N <= D ? u2 : pi - u2;
+                                st = r.d - alpha;
+                                if (st < 0.f) st += two_pi;
+                                en = fmaf(2.f, alpha, st);
+                                has = true;
+                            }
+                        }
+                    }
+                }
+            }
+            if (__any_sync(kFull, bur)) { buried = true; break; }
+            const unsigned m = __ballot_sync(kFull, has);
+            if (has) {
+                const int slot = narc + __popc(m & lt);
+                KeyArc arc;
+                arc.key = (__float_as_int(st) & ~0xff) | slot;
+                arc.en = en;
+                arcs[slot] = arc;
+                starts[slot] = st;
+                my_max = fmaxf(my_max, en);
+            }
+            narc += __popc(m);
+        }
+        if (buried) continue;
+        if (narc == 0) {
+            if (lane == 0) acc += (double)two_pi;
+            continue;
+        }
+        if (lane < 4) {                                    // sentinels so the merge can read 4 arcs at a time
+            KeyArc pad;
+            pad.key = 0x7f800000;
+            pad.en = 0.f;
+            arcs[narc + lane] = pad;
+        }
+        for (int o = 16; o; o >>= 1) my_max = fmaxf(my_max, __shfl_xor_sync(kFull, my_max, o));
+        const float W = fmaxf(my_max - two_pi, 0.f);       // [0, W) is covered by arcs that wrap past 2 pi
+        __syncwarp();
+        const float4 *quad = reinterpret_cast<const float4 *>(arcs);
+        const int n_quads = (narc + 3) >> 2;
+        for (int k = lane; k < narc; k += 32) {
+            const int my_key = arcs[k].key;
+            float P = W;
+            for (int g = 0; g < n_quads; ++g) {
+                const float4 lo = quad[2 * g], hi = quad[2 * g + 1];   // warp-uniform addresses: broadcast
+                if (__float_as_int(lo.x) < my_key) P = fmaxf(P, lo.y);
+                if (__float_as_int(lo.z) < my_key) P = fmaxf(P, lo.w);
+                if (__float_as_int(hi.x) < my_key) P = fmaxf(P, hi.y);
+                if (__float_as_int(hi.z) < my_key) P = fmaxf(P, hi.w);
+            }
+            acc += (double)fmaxf(starts[k] - P, 0.f);
+        }
+        if (lane == 0) acc += (double)fmaxf(two_pi - my_max, 0.f);
+        __syncwarp();
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    return delta * Ri_d * acc;
+}
+
 // ---- step 3: Shrake & Rupley ---------------------------------------------------------------------
 // fp32 decision band of this atom: the dot product and t each carry at most ~4e-7 * (|D|+|t|) of
 // rounding; every test closer than 10x that to the threshold is re-decided exactly in fp64.
@@ -310,17 +453,19 @@ __device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, 
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
 template <int ALG, typename T> struct WarpMem {
     Rec4<T> *recs;
-    Arc<T> *arcs;   // L&R only
+    Arc<T> *arcs;   // L&R only (cap + 4 entries)
+    T *starts;      // L&R fp32 fast path only
     int *cidx;      // S&R only
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
         arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 4) * sizeof(Arc<T>));
         cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
     }
 };
 
-template <int ALG, typename T>
+template <int ALG, typename T, bool FAST>
 __device__ __forceinline__ void finish_atom(const Workspace &ws, const IntegrateArgs &args, const WarpMem<ALG, T> &wm,
                                             const double4 *cand_base, const Self &s, int nn, int cap, int pos,
                                             bool allow_overflow, int lane)
@@ -337,7 +482,11 @@ __device__ __forceinline__ void finish_atom(const Workspace &ws, const Integrate
     if (s.R > 0.0) {
         if (ALG == 0) {
             lr_prepare<T>(wm.recs, nn, lane);
-            area = lr_atom<T>(wm.recs, wm.arcs, nn, s.R, args.resolution, lane);
+            if constexpr (FAST && sizeof(T) == 4)
+                area = lr_atom_fast(reinterpret_cast<const Rec4<float> *>(wm.recs), reinterpret_cast<KeyArc *>(wm.arcs),
+                                    reinterpret_cast<float *>(wm.starts), nn, s.R, args.resolution, lane);
+            else
+                area = lr_atom<T>(wm.recs, wm.arcs, nn, s.R, args.resolution, lane);
         } else {
             area = sr_atom<T>(wm.recs, wm.cidx, cand_base, nn, s, args.resolution, args.points_f, args.points_d, lane);
         }
@@ -420,7 +569,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, Integra
                     const int self_idx = off[4] + (pos - s_begin[4]);
                     const Self s = load_self(tile[self_idx]);
                     const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.recs, wm.cidx, 0, kNbCap, lane);
-                    finish_atom<ALG, T>(ws, args, wm, tile, s, nn, kNbCap, pos, true, lane);
+                    finish_atom<ALG, T, true>(ws, args, wm, tile, s, nn, kNbCap, pos, true, lane);
                 }
             } else if (active) {  // oversized neighbourhood: read the candidates straight from global memory
                 const Self s = load_self(ws.atoms[pos]);
@@ -428,7 +577,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, Integra
                 for (int r = 0; r < 9; ++r)
                     nn = gather_run<ALG, T>(ws.atoms + s_begin[r], s_count[r], r == 4 ? pos - s_begin[4] : -1, s_begin[r], s,
                                             wm.recs, wm.cidx, nn, kNbCap, lane);
-                finish_atom<ALG, T>(ws, args, wm, ws.atoms, s, nn, kNbCap, pos, true, lane);
+                finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, s, nn, kNbCap, pos, true, lane);
             }
         }
         __syncthreads();  // tile, s_item and s_begin/s_count are reused by the next item
@@ -463,7 +612,7 @@ __global__ void __launch_bounds__(128) k_overflow(Workspace ws, IntegrateArgs ar
             cell_run(ws, g, c[0], c[1], c[2], r, &b, &n);
             nn = gather_run<ALG, T>(ws.atoms + b, n, r == 4 ? pos - b : -1, b, s, wm.recs, wm.cidx, nn, list_cap, lane);
         }
-        finish_atom<ALG, T>(ws, args, wm, ws.atoms, s, nn, list_cap, pos, false, lane);
+        finish_atom<ALG, T, false>(ws, args, wm, ws.atoms, s, nn, list_cap, pos, false, lane);
         __syncwarp();
     }
 }

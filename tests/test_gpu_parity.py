@@ -161,7 +161,7 @@ def test_zero_probe(eng32):
 
 
 def test_crowded_neighbourhoods_take_the_overflow_path(eng32, eng64):
-    """> 160 neighbours per atom (smem list capacity) and > 768 atoms per 27-cell tile."""
+    """> 160 neighbours per atom (smem list capacity) and > 640 atoms per 27-cell tile."""
     rng = np.random.default_rng(9)
     x = rng.uniform(-4.0, 4.0, (1500, 3))
     r = rng.choice([1.2, 1.6, 1.9], 1500)
