@@ -85,11 +85,12 @@ template <> struct Consts<double> {
 
 template <int ALG, typename T> struct WarpLayout {
     // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
-    //   L&R: records + arcs (cap + 4 sentinel slots) + exact arc starts;  S&R: records + candidate indices
+    //   L&R: two record arrays (raw + z-sorted; once the raw one is consumed it holds the arcs of the
+    //        current slice: (cap + 4) arcs + cap exact starts fit in it)
+    //   S&R: records + candidate indices
     static __host__ __device__ constexpr size_t bytes(int cap)
     {
-        return ALG == 0 ? (size_t)cap * (sizeof(Rec4<T>) + sizeof(Arc<T>) + sizeof(T)) + 4 * sizeof(Arc<T>)
-                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
+        return ALG == 0 ? (size_t)cap * 2 * sizeof(Rec4<T>) : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
     }
 };
 
@@ -286,58 +287,79 @@ struct alignas(8) KeyArc {
     float en;   // start + 2 alpha (may exceed 2 pi: the arc wraps)
 };
 
+// raw {dx,dy,dz,R} -> {dz, R, dxy, beta}, written to `out` in ascending dz (rank sort: nn^2/32 compares
+// per lane, once per atom).  With the records z-sorted, the neighbours that can reach a slice at height z
+// are the contiguous window dz in (z - Rmax, z + Rmax), so a slice usually needs ONE round of 32 lanes
+// instead of ceil(nn/32).  Returns Rmax, the largest neighbour radius.
+__device__ __forceinline__ float lr_prepare_sorted(const Rec4<float> *raw, Rec4<float> *out, int nn, int lane)
+{
+    float rmax = 0.f;
+    for (int j = lane; j < nn; j += 32) {
+        const Rec4<float> r = raw[j];
+        int rank = 0;
+        for (int k = 0; k < nn; ++k) {
+            const float dzk = raw[k].c;                    // warp-uniform address: broadcast
+            rank += (dzk < r.c || (dzk == r.c && k < j)) ? 1 : 0;
+        }
+        Rec4<float> o;
+        o.a = r.c;
+        o.b = r.d;
+        o.c = sqrtf(r.a * r.a + r.b * r.b);                // src/nb.c:440
+        o.d = atan2f(r.b, r.a) + 3.141592653589793f;       // src/sasa_lr.c:337, hoisted out of the slice loop
+        out[rank] = o;
+        rmax = fmaxf(rmax, r.d);
+    }
+    for (int o = 16; o; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(kFull, rmax, o));
+    __syncwarp();
+    return rmax;
+}
+
 __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
-                                               double Ri_d, int ns, int lane)
+                                               float rmax, double Ri_d, int ns, int lane)
 {
     const float Ri = (float)Ri_d;
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
     const double delta = 2.0 * Ri_d / ns;
     const unsigned lt = lanemask_lt();
     double acc = 0.0;
+    int w_lo = 0, w_hi = 0;                                // window [w_lo, w_hi) of the z-sorted records
 
     for (int s = 0; s < ns; ++s) {
         const float zr = (float)(-Ri_d + (s + 0.5) * delta);
         const float az = fabsf(zr);
         const float a2 = (Ri - az) * (Ri + az);
         if (!(a2 > 0.f)) continue;
-        const float a = sqrtf(a2);                         // once per slice: keep the IEEE root
+        const float a = fast_sqrt(a2);
+        while (w_hi < nn && recs[w_hi].a - rmax < zr) ++w_hi;   // slices only move up: both ends only advance
+        while (w_lo < w_hi && recs[w_lo].a + rmax <= zr) ++w_lo;
         int narc = 0;
         bool buried = false;
         float my_max = 0.f;
-        for (int base = 0; base < nn; base += 32) {
+        for (int base = w_lo; base < w_hi; base += 32) {
             const int j = base + lane;
-            bool has = false, bur = false;
-            float st = 0.f, en = 0.f;
-            if (j < nn) {
-                const Rec4<float> r = recs[j];             // {dz, R, dxy, beta}
-                const float dj = fabsf(r.a - zr);
-                if (dj < r.b) {
-                    const float b = fast_sqrt((r.b - dj) * (r.b + dj));
-                    const float d = r.c;
-                    const float ab = a + b;
-                    const float f1 = ab - d;
-                    if (f1 > 0.f) {
-                        const float f3 = (d + a) - b;
-                        if (f3 < 0.f) {
-                            bur = true;
-                        } else {
-                            const float f2 = (d + b) - a;
-                            if (!(f2 < 0.f)) {
-                                const float N = f1 * f2, D = f3 * (ab + d);
-                                const float hi = fmaxf(N, D), lo = fminf(N, D);
-                                const float q = hi > 0.f ? lo * fast_rcp(hi) : 0.f;
-                                const float u2 = 2.f * atan_sqrt01(fminf(q, 1.f));
-                                const float alpha = N <= D ? u2 : pi - u2;
-                                st = r.d - alpha;
-                                if (st < 0.f) st += two_pi;
-                                en = fmaf(2.f, alpha, st);
-                                has = true;
-                            }
-                        }
-                    }
-                }
-            }
+            const bool valid = j < w_hi;
+            const Rec4<float> r = recs[valid ? j : w_lo];  // {dz, R, dxy, beta}
+            // straight-line: every lane evaluates everything, flags decide what counts
+            const float dj = fabsf(r.a - zr);
+            const float b2 = (r.b - dj) * (r.b + dj);      // Rj'^2; > 0  <=>  dj < Rj
+            const float b = fast_sqrt(fmaxf(b2, 0.f));
+            const float d = r.c;
+            const float ab = a + b;
+            const float f1 = ab - d;                       // > 0  <=> circles touch      (src/sasa_lr.c:324)
+            const float f3 = (d + a) - b;                  // < 0  <=> circle i inside j  (:327)
+            const float f2 = (d + b) - a;                  // < 0  <=> circle j inside i  (:331)
+            const bool touch = valid && b2 > 0.f && f1 > 0.f;
+            const bool bur = touch && f3 < 0.f;
+            const bool has = touch && !(f3 < 0.f) && !(f2 < 0.f);
             if (__any_sync(kFull, bur)) { buried = true; break; }
+            const float N = f1 * f2, D = f3 * (ab + d);
+            const float hi = fmaxf(N, D), lo = fminf(N, D);
+            const float q = hi > 0.f ? fminf(lo * fast_rcp(hi), 1.f) : 0.f;
+            const float u2 = 2.f * atan_sqrt01(q);
+            const float alpha = N <= D ? u2 : pi - u2;
+            float st = r.d - alpha;
+            st += st < 0.f ? two_pi : 0.f;
+            const float en = fmaf(2.f, alpha, st);
             const unsigned m = __ballot_sync(kFull, has);
             if (has) {
                 const int slot = narc + __popc(m & lt);
@@ -452,16 +474,23 @@ __device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, 
 
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
 template <int ALG, typename T> struct WarpMem {
-    Rec4<T> *recs;
-    Arc<T> *arcs;   // L&R only (cap + 4 entries)
-    T *starts;      // L&R fp32 fast path only
-    int *cidx;      // S&R only
+    Rec4<T> *recs;     // records the integrator reads
+    Rec4<T> *second;   // L&R: second record array (raw records in the fast path), later the arcs
+    Arc<T> *arcs;      // L&R: (cap + 4) arcs, aliases `second`
+    T *starts;         // L&R fp32 fast path: exact arc starts, behind the arcs
+    int *cidx;         // S&R only
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
-        arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        second = reinterpret_cast<Rec4<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        arcs = reinterpret_cast<Arc<T> *>(second);
         starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 4) * sizeof(Arc<T>));
         cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
+    }
+    // where gather_run() must put the raw records
+    template <bool FAST> __device__ __forceinline__ Rec4<T> *gather_target() const
+    {
+        return (ALG == 0 && FAST && sizeof(T) == 4) ? second : recs;
     }
 };
 
@@ -481,12 +510,15 @@ __device__ __forceinline__ void finish_atom(const Workspace &ws, const Integrate
     double area = 0.0;
     if (s.R > 0.0) {
         if (ALG == 0) {
-            lr_prepare<T>(wm.recs, nn, lane);
-            if constexpr (FAST && sizeof(T) == 4)
+            if constexpr (FAST && sizeof(T) == 4) {
+                const float rmax = lr_prepare_sorted(reinterpret_cast<const Rec4<float> *>(wm.second),
+                                                     reinterpret_cast<Rec4<float> *>(wm.recs), nn, lane);
                 area = lr_atom_fast(reinterpret_cast<const Rec4<float> *>(wm.recs), reinterpret_cast<KeyArc *>(wm.arcs),
-                                    reinterpret_cast<float *>(wm.starts), nn, s.R, args.resolution, lane);
-            else
+                                    reinterpret_cast<float *>(wm.starts), nn, rmax, s.R, args.resolution, lane);
+            } else {
+                lr_prepare<T>(wm.recs, nn, lane);
                 area = lr_atom<T>(wm.recs, wm.arcs, nn, s.R, args.resolution, lane);
+            }
         } else {
             area = sr_atom<T>(wm.recs, wm.cidx, cand_base, nn, s, args.resolution, args.points_f, args.points_d, lane);
         }
@@ -568,7 +600,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, Integra
                 if (active) {
                     const int self_idx = off[4] + (pos - s_begin[4]);
                     const Self s = load_self(tile[self_idx]);
-                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.recs, wm.cidx, 0, kNbCap, lane);
+                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.template gather_target<true>(), wm.cidx, 0, kNbCap, lane);
                     finish_atom<ALG, T, true>(ws, args, wm, tile, s, nn, kNbCap, pos, true, lane);
                 }
             } else if (active) {  // oversized neighbourhood: read the candidates straight from global memory
@@ -576,7 +608,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, Integra
                 int nn = 0;
                 for (int r = 0; r < 9; ++r)
                     nn = gather_run<ALG, T>(ws.atoms + s_begin[r], s_count[r], r == 4 ? pos - s_begin[4] : -1, s_begin[r], s,
-                                            wm.recs, wm.cidx, nn, kNbCap, lane);
+                                            wm.template gather_target<true>(), wm.cidx, nn, kNbCap, lane);
                 finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, s, nn, kNbCap, pos, true, lane);
             }
         }
