@@ -85,12 +85,11 @@ template <> struct Consts<double> {
 
 template <int ALG, typename T> struct WarpLayout {
     // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
-    //   L&R: two record arrays (raw + z-sorted; once the raw one is consumed it holds the arcs of the
-    //        current slice: (cap + 4) arcs + cap exact starts fit in it)
-    //   S&R: records + candidate indices
+    //   L&R: records + (cap + 36) arcs of the current slice + their exact starts;  S&R: records + candidate indices
     static __host__ __device__ constexpr size_t bytes(int cap)
     {
-        return ALG == 0 ? (size_t)cap * 2 * sizeof(Rec4<T>) : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
+        return ALG == 0 ? (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 36) * (sizeof(Arc<T>) + sizeof(T))
+                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
     }
 };
 
@@ -287,42 +286,46 @@ struct alignas(8) KeyArc {
     float en;   // start + 2 alpha (may exceed 2 pi: the arc wraps)
 };
 
-// raw {dx,dy,dz,R} -> {dz, R, dxy, beta}, written to `out` in ascending dz (rank sort: nn^2/32 compares
-// per lane, once per atom).  With the records z-sorted, the neighbours that can reach a slice at height z
-// are the contiguous window dz in (z - Rmax, z + Rmax), so a slice usually needs ONE round of 32 lanes
-// instead of ceil(nn/32).  Returns Rmax, the largest neighbour radius.
-__device__ __forceinline__ float lr_prepare_sorted(const Rec4<float> *raw, Rec4<float> *out, int nn, int lane)
+// Exposed length contributed by this lane's arcs: sum_k max(0, start_k - max(W, P_k)) with
+// P_k = max{ en_m : key_m < key_k }.  arcs[0..narc) hold (unique key, end); sentinels are appended so the
+// loop can read four arcs at a time.  All lanes must call it (it synchronises the warp).
+__device__ __forceinline__ float merge_keyed(KeyArc *arcs, const float *starts, int narc, float W, int lane)
 {
-    float rmax = 0.f;
-    for (int j = lane; j < nn; j += 32) {
-        const Rec4<float> r = raw[j];
-        int rank = 0;
-        for (int k = 0; k < nn; ++k) {
-            const float dzk = raw[k].c;                    // warp-uniform address: broadcast
-            rank += (dzk < r.c || (dzk == r.c && k < j)) ? 1 : 0;
-        }
-        Rec4<float> o;
-        o.a = r.c;
-        o.b = r.d;
-        o.c = sqrtf(r.a * r.a + r.b * r.b);                // src/nb.c:440
-        o.d = atan2f(r.b, r.a) + 3.141592653589793f;       // src/sasa_lr.c:337, hoisted out of the slice loop
-        out[rank] = o;
-        rmax = fmaxf(rmax, r.d);
+    if (lane < 4) {
+        KeyArc pad;
+        pad.key = 0x7f800000;
+        pad.en = 0.f;
+        arcs[narc + lane] = pad;
     }
-    for (int o = 16; o; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(kFull, rmax, o));
     __syncwarp();
-    return rmax;
+    const float4 *quad = reinterpret_cast<const float4 *>(arcs);
+    const int n_quads = (narc + 3) >> 2;
+    float sum = 0.f;
+    for (int k = lane; k < narc; k += 32) {
+        const int my_key = arcs[k].key;
+        float P = W;
+        for (int g = 0; g < n_quads; ++g) {
+            const float4 lo = quad[2 * g], hi = quad[2 * g + 1];   // warp-uniform addresses: broadcast
+            if (__float_as_int(lo.x) < my_key) P = fmaxf(P, lo.y);
+            if (__float_as_int(lo.z) < my_key) P = fmaxf(P, lo.w);
+            if (__float_as_int(hi.x) < my_key) P = fmaxf(P, hi.y);
+            if (__float_as_int(hi.z) < my_key) P = fmaxf(P, hi.w);
+        }
+        sum += fmaxf(starts[k] - P, 0.f);
+    }
+    return sum;
 }
 
+// General fp32 path (any neighbour count): all arcs of a slice are compacted to shared memory and merged
+// pairwise with unique integer keys.
 __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
-                                               float rmax, double Ri_d, int ns, int lane)
+                                               double Ri_d, int ns, int lane)
 {
     const float Ri = (float)Ri_d;
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
     const double delta = 2.0 * Ri_d / ns;
     const unsigned lt = lanemask_lt();
     double acc = 0.0;
-    int w_lo = 0, w_hi = 0;                                // window [w_lo, w_hi) of the z-sorted records
 
     for (int s = 0; s < ns; ++s) {
         const float zr = (float)(-Ri_d + (s + 0.5) * delta);
@@ -330,16 +333,13 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
         const float a2 = (Ri - az) * (Ri + az);
         if (!(a2 > 0.f)) continue;
         const float a = fast_sqrt(a2);
-        while (w_hi < nn && recs[w_hi].a - rmax < zr) ++w_hi;   // slices only move up: both ends only advance
-        while (w_lo < w_hi && recs[w_lo].a + rmax <= zr) ++w_lo;
         int narc = 0;
         bool buried = false;
         float my_max = 0.f;
-        for (int base = w_lo; base < w_hi; base += 32) {
+        for (int base = 0; base < nn; base += 32) {
             const int j = base + lane;
-            const bool valid = j < w_hi;
-            const Rec4<float> r = recs[valid ? j : w_lo];  // {dz, R, dxy, beta}
-            // straight-line: every lane evaluates everything, flags decide what counts
+            const bool valid = j < nn;
+            const Rec4<float> r = recs[valid ? j : 0];     // {dz, R, dxy, beta}
             const float dj = fabsf(r.a - zr);
             const float b2 = (r.b - dj) * (r.b + dj);      // Rj'^2; > 0  <=>  dj < Rj
             const float b = fast_sqrt(fmaxf(b2, 0.f));
@@ -364,7 +364,7 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
             if (has) {
                 const int slot = narc + __popc(m & lt);
                 KeyArc arc;
-                arc.key = (__float_as_int(st) & ~0xff) | slot;
+                arc.key = (__float_as_int(st) & ~0xff) | (slot & 0xff);
                 arc.en = en;
                 arcs[slot] = arc;
                 starts[slot] = st;
@@ -377,34 +377,185 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
             if (lane == 0) acc += (double)two_pi;
             continue;
         }
-        if (lane < 4) {                                    // sentinels so the merge can read 4 arcs at a time
-            KeyArc pad;
-            pad.key = 0x7f800000;
-            pad.en = 0.f;
-            arcs[narc + lane] = pad;
-        }
-        for (int o = 16; o; o >>= 1) my_max = fmaxf(my_max, __shfl_xor_sync(kFull, my_max, o));
-        const float W = fmaxf(my_max - two_pi, 0.f);       // [0, W) is covered by arcs that wrap past 2 pi
-        __syncwarp();
-        const float4 *quad = reinterpret_cast<const float4 *>(arcs);
-        const int n_quads = (narc + 3) >> 2;
-        for (int k = lane; k < narc; k += 32) {
-            const int my_key = arcs[k].key;
-            float P = W;
-            for (int g = 0; g < n_quads; ++g) {
-                const float4 lo = quad[2 * g], hi = quad[2 * g + 1];   // warp-uniform addresses: broadcast
-                if (__float_as_int(lo.x) < my_key) P = fmaxf(P, lo.y);
-                if (__float_as_int(lo.z) < my_key) P = fmaxf(P, lo.w);
-                if (__float_as_int(hi.x) < my_key) P = fmaxf(P, hi.y);
-                if (__float_as_int(hi.z) < my_key) P = fmaxf(P, hi.w);
-            }
-            acc += (double)fmaxf(starts[k] - P, 0.f);
-        }
+        my_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(my_max)));  // non-negative floats order like uints
+        acc += (double)merge_keyed(arcs, starts, narc, fmaxf(my_max - two_pi, 0.f), lane);
         if (lane == 0) acc += (double)fmaxf(two_pi - my_max, 0.f);
         __syncwarp();
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
     return delta * Ri_d * acc;
+}
+
+// ---- step 2c: the common case, at most 64 neighbours ------------------------------------------------
+// The (z-sorted) records live in REGISTERS, two per lane, for all slices of the atom.  Per slice:
+//   1. both halves evaluate their circle-circle configuration; a half whose neighbours are all out of
+//      z-range is skipped (the records are z-sorted, so low slices skip the upper half and vice versa);
+//   2. one vote: some circle swallows the slice circle -> the slice is buried (src/sasa_lr.c:327);
+//   3. angles are measured in SECTORS (1/32 of the circle, so pi is exactly 16): every arc marks the
+//      sectors it covers completely in a 32-bit mask, one REDUX.OR gives the sectors covered by a single
+//      arc.  If that is all 32, the slice exposes nothing and we are done — on a dense globule this settles
+//      ~90 % of the slices that survive step 2;
+//   4. otherwise only arcs with an end in an uncovered sector can matter.  They, plus one synthetic arc per
+//      run of covered sectors, are compacted (typically 2-4 arcs) and merged exactly as in lr_atom_fast.
+// Exactness: a sector counts as covered only if ONE arc contains it entirely (integer sector borders are
+// exact in fp32), so replacing the arcs inside covered sectors by the sectors themselves does not change
+// the union.
+__device__ __forceinline__ void lr_prepare_sorted64(Rec4<float> *recs, int nn, int lane)
+{
+    const float kS = 5.092958178940651f;                   // sectors per radian
+    Rec4<float> o[2];
+    int rank[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        rank[h] = -1;
+        if (j < nn) {
+            const Rec4<float> r = recs[j];                 // raw {dx, dy, dz, R}
+            int rk = 0;
+            for (int k = 0; k < nn; ++k) {
+                const float dzk = recs[k].c;               // warp-uniform address: broadcast
+                rk += (dzk < r.c || (dzk == r.c && k < j)) ? 1 : 0;
+            }
+            rank[h] = rk;
+            o[h].a = r.c;
+            o[h].b = r.d;
+            o[h].c = sqrtf(r.a * r.a + r.b * r.b);         // src/nb.c:440
+            o[h].d = (atan2f(r.b, r.a) + 3.141592653589793f) * kS;   // beta (src/sasa_lr.c:337), hoisted, in sectors
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (rank[h] >= 0) recs[rank[h]] = o[h];
+    __syncwarp();
+}
+
+struct HalfArc {
+    float st, en;     // sectors; st in [0,32), en in [st, st+32]
+    bool has, bur;
+};
+
+__device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, float zr, float a)
+{
+    HalfArc h;
+    h.st = 0.f; h.en = 0.f; h.has = false; h.bur = false;
+    const float dj = fabsf(r.a - zr);
+    const float b2 = (r.b - dj) * (r.b + dj);
+    const bool act = valid && b2 > 0.f;
+    if (__any_sync(kFull, act)) {
+        const float b = fast_sqrt(fmaxf(b2, 0.f));
+        const float d = r.c;
+        const float ab = a + b;
+        const float f1 = ab - d, f3 = (d + a) - b, f2 = (d + b) - a;
+        const bool touch = act && f1 > 0.f;
+        h.bur = touch && f3 < 0.f;
+        h.has = touch && !(f3 < 0.f) && !(f2 < 0.f);
+        // N, D kept in st/en until the burial vote is over
+        h.st = f1 * f2;
+        h.en = f3 * (ab + d);
+    }
+    return h;
+}
+
+__device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
+{
+    // alpha in sectors: (32/2pi) * 2 atan(sqrt(q)); pi = 16 sectors
+    const float N = h.st, D = h.en;
+    const float hi = fmaxf(N, D), lo = fminf(N, D);
+    const float q = hi > 0.f ? fminf(lo * fast_rcp(hi), 1.f) : 0.f;
+    const float u2 = 10.185916357881302f * atan_sqrt01(q);
+    const float alpha = N <= D ? u2 : 16.f - u2;
+    float st = beta_s - alpha;
+    st += st < 0.f ? 32.f : 0.f;
+    st = st >= 32.f ? st - 32.f : st;
+    const float en = fmaf(2.f, alpha, st);
+    h.st = st;
+    h.en = en;
+    // sectors completely inside [st, en)
+    const int js = (int)st;
+    const int jf = js + ((float)js < st ? 1 : 0);
+    const int cnt = (int)en - jf;
+    unsigned mask = cnt >= 32 ? 0xffffffffu : __funnelshift_l((1u << (cnt & 31)) - 1u, (1u << (cnt & 31)) - 1u, jf & 31);
+    return (h.has && cnt > 0) ? mask : 0u;
+}
+
+__device__ __forceinline__ double lr_atom_fast64(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
+                                                 double Ri_d, int ns, int lane)
+{
+    const float Ri = (float)Ri_d;
+    const double delta = 2.0 * Ri_d / ns;
+    const unsigned lt = lanemask_lt();
+    const bool v0 = lane < nn, v1 = lane + 32 < nn;
+    const bool two_halves = nn > 32;
+    const Rec4<float> r0 = recs[v0 ? lane : 0];
+    const Rec4<float> r1 = recs[v1 ? lane + 32 : 0];
+    double acc = 0.0;                                      // exposed angle in sectors
+
+    for (int s = 0; s < ns; ++s) {
+        const float zr = (float)(-Ri_d + (s + 0.5) * delta);
+        const float az = fabsf(zr);
+        const float a2 = (Ri - az) * (Ri + az);
+        if (!(a2 > 0.f)) continue;
+        const float a = fast_sqrt(a2);
+        HalfArc h0 = half_eval(r0, v0, zr, a);
+        HalfArc h1;
+        h1.st = 0.f; h1.en = 0.f; h1.has = false; h1.bur = false;
+        if (two_halves) h1 = half_eval(r1, v1, zr, a);
+        if (__any_sync(kFull, h0.bur || h1.bur)) continue;                 // buried slice
+        const unsigned any0 = __ballot_sync(kFull, h0.has), any1 = __ballot_sync(kFull, h1.has);
+        if ((any0 | any1) == 0u) {                                         // free circle
+            if (lane == 0) acc += 32.0;
+            continue;
+        }
+        unsigned mask = 0u;
+        if (any0) mask |= half_finish(h0, r0.d);
+        if (any1) mask |= half_finish(h1, r1.d);
+        const unsigned full = __reduce_or_sync(kFull, mask);
+        if (full == 0xffffffffu) continue;                                 // every sector inside some arc
+        // arcs with an end in an uncovered sector, plus one synthetic arc per run of covered sectors
+        const bool rel0 = h0.has && (!((full >> ((int)h0.st & 31)) & 1u) || !((full >> ((int)h0.en & 31)) & 1u));
+        const bool rel1 = h1.has && (!((full >> ((int)h1.st & 31)) & 1u) || !((full >> ((int)h1.en & 31)) & 1u));
+        const bool syn = ((full >> lane) & 1u) && !((full >> ((lane + 31) & 31)) & 1u);
+        const unsigned b0 = __ballot_sync(kFull, rel0), b1 = __ballot_sync(kFull, rel1), b2 = __ballot_sync(kFull, syn);
+        const int n0 = __popc(b0), n1 = __popc(b1), narc = n0 + n1 + __popc(b2);
+        float my_max = 0.f;
+        if (rel0) {
+            const int slot = __popc(b0 & lt);
+            KeyArc arc;
+            arc.key = (__float_as_int(h0.st) & ~0xff) | slot;
+            arc.en = h0.en;
+            arcs[slot] = arc;
+            starts[slot] = h0.st;
+            my_max = h0.en;
+        }
+        if (rel1) {
+            const int slot = n0 + __popc(b1 & lt);
+            KeyArc arc;
+            arc.key = (__float_as_int(h1.st) & ~0xff) | slot;
+            arc.en = h1.en;
+            arcs[slot] = arc;
+            starts[slot] = h1.st;
+            my_max = fmaxf(my_max, h1.en);
+        }
+        if (syn) {
+            const unsigned rot = __funnelshift_r(full, full, lane);        // covered run starts at bit 0
+            const int ones = __ffs(~rot) - 1;                              // full != all ones here
+            const int slot = n0 + n1 + __popc(b2 & lt);
+            const float st = (float)lane, en = (float)(lane + ones);
+            KeyArc arc;
+            arc.key = (__float_as_int(st) & ~0xff) | slot;
+            arc.en = en;
+            arcs[slot] = arc;
+            starts[slot] = st;
+            my_max = fmaxf(my_max, en);
+        }
+        my_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(my_max)));
+        acc += (double)merge_keyed(arcs, starts, narc, fmaxf(my_max - 32.f, 0.f), lane);
+        if (lane == 0) acc += (double)fmaxf(32.f - my_max, 0.f);
+        __syncwarp();
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    return delta * Ri_d * acc * 0.19634954084936207;       // sectors -> radians (2 pi / 32)
 }
 
 // ---- step 3: Shrake & Rupley ---------------------------------------------------------------------
@@ -474,23 +625,16 @@ __device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, 
 
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
 template <int ALG, typename T> struct WarpMem {
-    Rec4<T> *recs;     // records the integrator reads
-    Rec4<T> *second;   // L&R: second record array (raw records in the fast path), later the arcs
-    Arc<T> *arcs;      // L&R: (cap + 4) arcs, aliases `second`
-    T *starts;         // L&R fp32 fast path: exact arc starts, behind the arcs
+    Rec4<T> *recs;
+    Arc<T> *arcs;      // L&R: cap + 36 arcs of the current slice
+    T *starts;         // L&R fp32 fast path: exact arc starts
     int *cidx;         // S&R only
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
-        second = reinterpret_cast<Rec4<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
-        arcs = reinterpret_cast<Arc<T> *>(second);
-        starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 4) * sizeof(Arc<T>));
+        arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 36) * sizeof(Arc<T>));
         cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
-    }
-    // where gather_run() must put the raw records
-    template <bool FAST> __device__ __forceinline__ Rec4<T> *gather_target() const
-    {
-        return (ALG == 0 && FAST && sizeof(T) == 4) ? second : recs;
     }
 };
 
@@ -511,10 +655,16 @@ __device__ __forceinline__ void finish_atom(const Workspace &ws, const Integrate
     if (s.R > 0.0) {
         if (ALG == 0) {
             if constexpr (FAST && sizeof(T) == 4) {
-                const float rmax = lr_prepare_sorted(reinterpret_cast<const Rec4<float> *>(wm.second),
-                                                     reinterpret_cast<Rec4<float> *>(wm.recs), nn, lane);
-                area = lr_atom_fast(reinterpret_cast<const Rec4<float> *>(wm.recs), reinterpret_cast<KeyArc *>(wm.arcs),
-                                    reinterpret_cast<float *>(wm.starts), nn, rmax, s.R, args.resolution, lane);
+                Rec4<float> *recs = reinterpret_cast<Rec4<float> *>(wm.recs);
+                KeyArc *arcs = reinterpret_cast<KeyArc *>(wm.arcs);
+                float *starts = reinterpret_cast<float *>(wm.starts);
+                if (nn <= 64) {
+                    lr_prepare_sorted64(recs, nn, lane);
+                    area = lr_atom_fast64(recs, arcs, starts, nn, s.R, args.resolution, lane);
+                } else {
+                    lr_prepare<float>(recs, nn, lane);
+                    area = lr_atom_fast(recs, arcs, starts, nn, s.R, args.resolution, lane);
+                }
             } else {
                 lr_prepare<T>(wm.recs, nn, lane);
                 area = lr_atom<T>(wm.recs, wm.arcs, nn, s.R, args.resolution, lane);
@@ -553,7 +703,7 @@ __device__ __forceinline__ void cell_run(const Workspace &ws, const GridDesc &g,
 }
 
 template <int ALG, typename T>
-__global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, IntegrateArgs args)
+__global__ void __launch_bounds__(kCtaThreads, 4) k_integrate(Workspace ws, IntegrateArgs args)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     double4 *tile = reinterpret_cast<double4 *>(smem);
@@ -600,7 +750,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, Integra
                 if (active) {
                     const int self_idx = off[4] + (pos - s_begin[4]);
                     const Self s = load_self(tile[self_idx]);
-                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.template gather_target<true>(), wm.cidx, 0, kNbCap, lane);
+                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.recs, wm.cidx, 0, kNbCap, lane);
                     finish_atom<ALG, T, true>(ws, args, wm, tile, s, nn, kNbCap, pos, true, lane);
                 }
             } else if (active) {  // oversized neighbourhood: read the candidates straight from global memory
@@ -608,7 +758,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_integrate(Workspace ws, Integra
                 int nn = 0;
                 for (int r = 0; r < 9; ++r)
                     nn = gather_run<ALG, T>(ws.atoms + s_begin[r], s_count[r], r == 4 ? pos - s_begin[4] : -1, s_begin[r], s,
-                                            wm.template gather_target<true>(), wm.cidx, nn, kNbCap, lane);
+                                            wm.recs, wm.cidx, nn, kNbCap, lane);
                 finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, s, nn, kNbCap, pos, true, lane);
             }
         }
