@@ -22,9 +22,10 @@
 
 namespace fsb200 {
 
-constexpr int kWarpsPerCta = 8;             // one atom per warp, one work item = up to 8 atoms of a cell
+constexpr int kWarpsPerCta = 14;            // warps claim atoms dynamically from the CTA's ring of staged tiles
 constexpr int kCtaThreads = kWarpsPerCta * 32;
-constexpr int kItemAtoms = kWarpsPerCta;
+constexpr int kRingSlots = 2;               // tiles in flight per CTA
+constexpr int kItemAtoms = 16;              // one work item = up to 16 consecutive atoms of one cell
 constexpr int kTileCap = 640;               // atoms of the 27-cell neighbourhood staged in smem (20 KB)
 constexpr int kNbCap = 160;                 // per-warp neighbour list capacity in smem
 constexpr int kCellsPerAtomCap = 2;         // grid budget: cells <= 2*n_k + 64 per structure

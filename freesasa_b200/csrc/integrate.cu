@@ -83,12 +83,16 @@ template <> struct Consts<double> {
     static __device__ __forceinline__ double pi() { return 3.141592653589793; }
 };
 
+// arcs one slice can produce: every neighbour (+4 sentinels) in the general paths, at most
+// 64 + 32 synthetic + 4 sentinels in the <= 64-neighbour path
+__host__ __device__ constexpr int arc_cap(int cap) { return cap + 4 > 100 ? cap + 4 : 100; }
+
 template <int ALG, typename T> struct WarpLayout {
     // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
-    //   L&R: records + (cap + 36) arcs of the current slice + their exact starts;  S&R: records + candidate indices
+    //   L&R: records + arc_cap(cap) arcs of the current slice + their exact starts;  S&R: records + candidate indices
     static __host__ __device__ constexpr size_t bytes(int cap)
     {
-        return ALG == 0 ? (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 36) * (sizeof(Arc<T>) + sizeof(T))
+        return ALG == 0 ? (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * (sizeof(Arc<T>) + sizeof(T))
                         : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
     }
 };
@@ -626,14 +630,14 @@ __device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, 
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
 template <int ALG, typename T> struct WarpMem {
     Rec4<T> *recs;
-    Arc<T> *arcs;      // L&R: cap + 36 arcs of the current slice
+    Arc<T> *arcs;      // L&R: arc_cap(cap) arcs of the current slice
     T *starts;         // L&R fp32 fast path: exact arc starts
     int *cidx;         // S&R only
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
         arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
-        starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)(cap + 36) * sizeof(Arc<T>));
+        starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * sizeof(Arc<T>));
         cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
     }
 };
@@ -702,67 +706,155 @@ __device__ __forceinline__ void cell_run(const Workspace &ws, const GridDesc &g,
     *count = e - b;
 }
 
+// ---- the persistent kernel: a ring of TMA-staged tiles, warps claim atoms one by one -------------------
+// Each CTA owns kRingSlots tile buffers.  A slot holds one work item (<= kItemAtoms atoms of one cell) and
+// its staged 27-cell neighbourhood.  Warps are NOT in lockstep (round 1, first version: 40 % of all warp
+// samples sat in the per-item __syncthreads because buried atoms finish long before surface atoms): a warp
+// waits for a slot's mbarrier, claims atoms of that item through a shared-memory counter until none are
+// left, then leaves the slot; the LAST warp to leave refills the slot with the next item of the global
+// queue (nine cp.async.bulk copies completing on the slot's mbarrier) while the other warps are already
+// working in the next slot.  The only waiting left is for a slot whose refill is still in flight.
+struct Slot {
+    int valid;        // 0: the global queue was empty when this slot was (re)filled
+    int first;        // first sorted position of the item
+    int n_atoms;      // atoms in the item
+    int next;         // next unclaimed atom (shared-memory atomic)
+    int done;         // warps that have left this slot
+    int total;        // candidates in the neighbourhood
+    int staged;       // 1: neighbourhood is in the slot's tile; 0: too large, read global memory
+    int self_off;     // tile index of sorted position p is self_off + p
+    int begin[9], count[9];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// executed by one full warp
+__device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateArgs &args, int n_items, Slot *sl,
+                                          double4 *tile, uint64_t *bar, int lane)
+{
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(ws.counters + kCtrQueue, 1);
+        idx = __shfl_sync(kFull, idx, 0);
+        if (idx >= n_items) {
+            if (lane == 0) {
+                sl->valid = 0;
+                sl->done = 0;
+                __threadfence_block();
+                mbar_arrive(bar);
+            }
+            return;
+        }
+        const Item it = ws.items[idx];
+        if (!(it.first < args.shard_end && it.first + it.count > args.shard_begin)) continue;  // another shard's
+        const GridDesc &g = ws.grid[it.sid];
+        const int cx = it.cell % g.dim[0], cy = (it.cell / g.dim[0]) % g.dim[1], cz = it.cell / (g.dim[0] * g.dim[1]);
+        int b = 0, n = 0;
+        if (lane < 9) cell_run(ws, g, cx, cy, cz, lane, &b, &n);
+        int incl = n;                                      // inclusive prefix sum over lanes 0..8
+        for (int o = 1; o < 16; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int off = incl - n;
+        const int total = __shfl_sync(kFull, incl, 8);
+        const int off4 = __shfl_sync(kFull, off, 4), b4 = __shfl_sync(kFull, b, 4);
+        const bool staged = total <= kTileCap;
+        if (lane < 9) {
+            sl->begin[lane] = b;
+            sl->count[lane] = n;
+        }
+        if (lane == 0) {
+            sl->valid = 1;
+            sl->first = it.first;
+            sl->n_atoms = it.count;
+            sl->next = 0;
+            sl->done = 0;
+            sl->total = total;
+            sl->staged = staged ? 1 : 0;
+            sl->self_off = off4 - b4;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (staged) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old tile vs. async writes
+                mbar_expect_tx(bar, (uint32_t)total * (uint32_t)sizeof(double4));
+            }
+            __syncwarp();
+            if (lane < 9 && n > 0) tma_load_1d(tile + off, ws.atoms + b, (uint32_t)n * (uint32_t)sizeof(double4), bar);
+        } else if (lane == 0) {
+            mbar_arrive(bar);
+        }
+        return;
+    }
+}
+
 template <int ALG, typename T>
-__global__ void __launch_bounds__(kCtaThreads, 4) k_integrate(Workspace ws, IntegrateArgs args)
+__global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, IntegrateArgs args)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    double4 *tile = reinterpret_cast<double4 *>(smem);
-    __shared__ uint64_t bar;
-    __shared__ int s_item;
-    __shared__ int s_begin[9], s_count[9];
+    __shared__ uint64_t full[kRingSlots];
+    __shared__ Slot slots[kRingSlots];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *warp_mem = smem + (size_t)kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
+    double4 *tiles = reinterpret_cast<double4 *>(smem);
+    unsigned char *warp_mem = smem + (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
+    const WarpMem<ALG, T> wm(warp_mem, kNbCap);
     const int n_items = ws.counters[kCtrItems];
-    if (tid == 0) mbar_init(&bar, 1);
+    if (tid == 0)
+        for (int s = 0; s < kRingSlots; ++s) mbar_init(&full[s], 1);
     __syncthreads();
-    uint32_t parity = 0;
+    if (warp == 0)
+        for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], lane);
 
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(ws.counters + kCtrQueue, 1);
-        __syncthreads();
-        const int item_idx = s_item;
-        if (item_idx >= n_items) break;
-        const Item it = ws.items[item_idx];
-        const bool mine = it.first < args.shard_end && it.first + it.count > args.shard_begin;
-        if (mine) {
-            const GridDesc &g = ws.grid[it.sid];
-            const int cx = it.cell % g.dim[0], cy = (it.cell / g.dim[0]) % g.dim[1], cz = it.cell / (g.dim[0] * g.dim[1]);
-            if (tid < 9) cell_run(ws, g, cx, cy, cz, tid, &s_begin[tid], &s_count[tid]);
-            __syncthreads();
-            int off[10];
-            off[0] = 0;
-            for (int r = 0; r < 9; ++r) off[r + 1] = off[r] + s_count[r];
-            const int total = off[9];
-            const bool staged = total <= kTileCap;
-            const int pos = it.first + warp;
-            const bool active = warp < it.count && pos >= args.shard_begin && pos < args.shard_end;
-            const WarpMem<ALG, T> wm(warp_mem, kNbCap);
-            if (staged) {
-                if (tid == 0) {
-                    mbar_expect_tx(&bar, (uint32_t)total * (uint32_t)sizeof(double4));
+    int dead = 0;
+    for (int seq = 0;; ++seq) {
+        const int s = seq % kRingSlots;
+        Slot *sl = &slots[s];
+        double4 *tile = tiles + (size_t)s * kTileCap;
+        mbar_wait(&full[s], (uint32_t)(seq / kRingSlots) & 1u);
+        if (sl->valid) {
+            dead = 0;
+            const int first = sl->first, n_atoms = sl->n_atoms, total = sl->total, self_off = sl->self_off;
+            const bool staged = sl->staged != 0;
+            for (;;) {
+                int a = 0;
+                if (lane == 0) a = atomicAdd(&sl->next, 1);
+                a = __shfl_sync(kFull, a, 0);
+                if (a >= n_atoms) break;
+                const int pos = first + a;
+                if (pos < args.shard_begin || pos >= args.shard_end) continue;
+                if (staged) {
+                    const int self_idx = self_off + pos;
+                    const Self me = load_self(tile[self_idx]);
+                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, me, wm.recs, wm.cidx, 0, kNbCap, lane);
+                    finish_atom<ALG, T, true>(ws, args, wm, tile, me, nn, kNbCap, pos, true, lane);
+                } else {  // oversized neighbourhood: read the candidates straight from global memory
+                    const Self me = load_self(ws.atoms[pos]);
+                    int nn = 0;
                     for (int r = 0; r < 9; ++r)
-                        if (s_count[r] > 0)
-                            tma_load_1d(tile + off[r], ws.atoms + s_begin[r], (uint32_t)s_count[r] * (uint32_t)sizeof(double4), &bar);
+                        nn = gather_run<ALG, T>(ws.atoms + sl->begin[r], sl->count[r], r == 4 ? pos - sl->begin[4] : -1, sl->begin[r], me,
+                                                wm.recs, wm.cidx, nn, kNbCap, lane);
+                    finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane);
                 }
-                mbar_wait(&bar, parity);
-                parity ^= 1;
-                if (active) {
-                    const int self_idx = off[4] + (pos - s_begin[4]);
-                    const Self s = load_self(tile[self_idx]);
-                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, s, wm.recs, wm.cidx, 0, kNbCap, lane);
-                    finish_atom<ALG, T, true>(ws, args, wm, tile, s, nn, kNbCap, pos, true, lane);
-                }
-            } else if (active) {  // oversized neighbourhood: read the candidates straight from global memory
-                const Self s = load_self(ws.atoms[pos]);
-                int nn = 0;
-                for (int r = 0; r < 9; ++r)
-                    nn = gather_run<ALG, T>(ws.atoms + s_begin[r], s_count[r], r == 4 ? pos - s_begin[4] : -1, s_begin[r], s,
-                                            wm.recs, wm.cidx, nn, kNbCap, lane);
-                finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, s, nn, kNbCap, pos, true, lane);
+                __syncwarp();
             }
+        } else {
+            ++dead;
         }
-        __syncthreads();  // tile, s_item and s_begin/s_count are reused by the next item
+        __syncwarp();
+        int d = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            d = atomicAdd(&sl->done, 1);
+        }
+        d = __shfl_sync(kFull, d, 0);
+        if (dead == kRingSlots) break;                     // a full turn of empty slots: the queue is drained
+        if (d == kWarpsPerCta - 1) fill_slot(ws, args, n_items, sl, tile, &full[s], lane);
     }
 }
 
@@ -801,7 +893,7 @@ __global__ void __launch_bounds__(128) k_overflow(Workspace ws, IntegrateArgs ar
 
 template <int ALG, typename T> size_t cta_smem_bytes()
 {
-    return (size_t)kTileCap * sizeof(double4) + (size_t)kWarpsPerCta * WarpLayout<ALG, T>::bytes(kNbCap);
+    return (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)kWarpsPerCta * WarpLayout<ALG, T>::bytes(kNbCap);
 }
 
 template <int ALG, typename T> int configure_and_occupancy(int device)
