@@ -707,33 +707,41 @@ __device__ __forceinline__ void cell_run(const Workspace &ws, const GridDesc &g,
 }
 
 // ---- the persistent kernel: a ring of TMA-staged tiles, warps claim atoms one by one -------------------
-// Each CTA owns kRingSlots tile buffers.  A slot holds one work item (<= kItemAtoms atoms of one cell) and
-// its staged 27-cell neighbourhood.  Warps are NOT in lockstep (round 1, first version: 40 % of all warp
-// samples sat in the per-item __syncthreads because buried atoms finish long before surface atoms): a warp
-// waits for a slot's mbarrier, claims atoms of that item through a shared-memory counter until none are
-// left, then leaves the slot; the LAST warp to leave refills the slot with the next item of the global
-// queue (nine cp.async.bulk copies completing on the slot's mbarrier) while the other warps are already
-// working in the next slot.  The only waiting left is for a slot whose refill is still in flight.
+// Each CTA owns kRingSlots tile buffers.  A "fill" is one work item (<= kItemAtoms atoms of one cell) plus
+// its 27-cell neighbourhood, staged into the slot fill % kRingSlots by nine cp.async.bulk copies that
+// complete on the slot's mbarrier.  Fills are numbered 0,1,2,... per CTA and `cur` is the fill currently
+// open for claiming.  A warp
+//   1. reads cur, waits for that fill's mbarrier phase, claims one atom with a compare-and-swap on the
+//      slot's packed (fill number, next atom) word — a warp can therefore never claim from a slot that has
+//      moved on, however long it was away;
+//   2. gathers the atom's neighbours from the tile into its private list.  That is the LAST use of the tile:
+//      the warp that completes the last gather of a fill immediately refills the slot with fill + kRingSlots
+//      from the global queue, and only then
+//   3. integrates the atom (the long part: slices or test points) — nobody waits for it.
+// History (profiles/): per-item __syncthreads cost 40 % of all warp samples because buried atoms finish long
+// before surface atoms; a first ring that refilled a slot only after every warp had LEFT it still left
+// 18 % of the samples (and 25 % of the issued instructions) in the mbarrier wait.
 struct Slot {
-    int valid;        // 0: the global queue was empty when this slot was (re)filled
+    int claim;        // (fill & 0xffff) << 16 | next unclaimed atom
+    int gathered;     // atoms of this fill whose neighbour gather is complete
+    int n_atoms;      // atoms in the item (0 for a dead slot)
+    int dead;         // the global queue was empty when this slot was last refilled: no more fills here
     int first;        // first sorted position of the item
-    int n_atoms;      // atoms in the item
-    int next;         // next unclaimed atom (shared-memory atomic)
-    int done;         // warps that have left this slot
     int total;        // candidates in the neighbourhood
     int staged;       // 1: neighbourhood is in the slot's tile; 0: too large, read global memory
     int self_off;     // tile index of sorted position p is self_off + p
-    int begin[9], count[9];
+    int begin[9], count[9], off[9];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+__device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 
-// executed by one full warp
+// executed by one full warp: stage fill number `fill` into slot sl
 __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateArgs &args, int n_items, Slot *sl,
-                                          double4 *tile, uint64_t *bar, int lane)
+                                          double4 *tile, uint64_t *bar, int fill, int lane)
 {
     for (;;) {
         int idx = 0;
@@ -741,8 +749,10 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
         idx = __shfl_sync(kFull, idx, 0);
         if (idx >= n_items) {
             if (lane == 0) {
-                sl->valid = 0;
-                sl->done = 0;
+                sl->n_atoms = 0;
+                sl->dead = 1;
+                sl->gathered = 0;
+                sl->claim = (fill & 0xffff) << 16;
                 __threadfence_block();
                 mbar_arrive(bar);
             }
@@ -766,16 +776,16 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
         if (lane < 9) {
             sl->begin[lane] = b;
             sl->count[lane] = n;
+            sl->off[lane] = off;
         }
         if (lane == 0) {
-            sl->valid = 1;
-            sl->first = it.first;
             sl->n_atoms = it.count;
-            sl->next = 0;
-            sl->done = 0;
+            sl->gathered = 0;
+            sl->first = it.first;
             sl->total = total;
             sl->staged = staged ? 1 : 0;
             sl->self_off = off4 - b4;
+            sl->claim = (fill & 0xffff) << 16;
         }
         __threadfence_block();
         __syncwarp();
@@ -799,62 +809,90 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[kRingSlots];
     __shared__ Slot slots[kRingSlots];
+    __shared__ int cur;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double4 *tiles = reinterpret_cast<double4 *>(smem);
     unsigned char *warp_mem = smem + (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
     const WarpMem<ALG, T> wm(warp_mem, kNbCap);
     const int n_items = ws.counters[kCtrItems];
-    if (tid == 0)
-        for (int s = 0; s < kRingSlots; ++s) mbar_init(&full[s], 1);
+    if (tid == 0) {
+        cur = 0;
+        for (int s = 0; s < kRingSlots; ++s) {
+            slots[s].dead = 0;
+            mbar_init(&full[s], 1);
+        }
+    }
     __syncthreads();
     if (warp == 0)
-        for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], lane);
+        for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], s, lane);
 
-    int dead = 0;
-    for (int seq = 0;; ++seq) {
-        const int s = seq % kRingSlots;
+    for (;;) {
+        // ---- claim one atom (lane 0 negotiates, the warp follows) ----------------------------------------
+        int code = 0, f = 0, a = 0;                        // code 0: look again, 1: atom claimed, 2: all work done
+        if (lane == 0) {
+            f = ld_volatile(&cur);
+            Slot *sl = &slots[f % kRingSlots];
+            if (ld_volatile(&sl->dead)) {
+                bool all = true;
+                for (int t = 0; t < kRingSlots; ++t) all = all && ld_volatile(&slots[t].dead) != 0;
+                if (all) code = 2;
+                else atomicCAS(&cur, f, f + 1);
+            } else {
+                mbar_wait(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u);
+                const int w = ld_volatile(&sl->claim);
+                if (((unsigned)w >> 16) == (unsigned)(f & 0xffff)) {
+                    a = w & 0xffff;
+                    if (a >= ld_volatile(&sl->n_atoms)) atomicCAS(&cur, f, f + 1);         // fill exhausted: open the next one
+                    else if (atomicCAS(&sl->claim, w, w + 1) == w) code = 1;
+                }
+            }
+        }
+        code = __shfl_sync(kFull, code, 0);
+        if (code == 2) break;
+        if (code == 0) continue;
+        f = __shfl_sync(kFull, f, 0);
+        a = __shfl_sync(kFull, a, 0);
+        const int s = f % kRingSlots;
         Slot *sl = &slots[s];
         double4 *tile = tiles + (size_t)s * kTileCap;
-        mbar_wait(&full[s], (uint32_t)(seq / kRingSlots) & 1u);
-        if (sl->valid) {
-            dead = 0;
-            const int first = sl->first, n_atoms = sl->n_atoms, total = sl->total, self_off = sl->self_off;
-            const bool staged = sl->staged != 0;
-            for (;;) {
-                int a = 0;
-                if (lane == 0) a = atomicAdd(&sl->next, 1);
-                a = __shfl_sync(kFull, a, 0);
-                if (a >= n_atoms) break;
-                const int pos = first + a;
-                if (pos < args.shard_begin || pos >= args.shard_end) continue;
-                if (staged) {
-                    const int self_idx = self_off + pos;
-                    const Self me = load_self(tile[self_idx]);
-                    const int nn = gather_run<ALG, T>(tile, total, self_idx, 0, me, wm.recs, wm.cidx, 0, kNbCap, lane);
-                    finish_atom<ALG, T, true>(ws, args, wm, tile, me, nn, kNbCap, pos, true, lane);
-                } else {  // oversized neighbourhood: read the candidates straight from global memory
-                    const Self me = load_self(ws.atoms[pos]);
-                    int nn = 0;
+        mbar_wait(&full[s], (uint32_t)(f / kRingSlots) & 1u);     // every lane observes the completed phase (immediate)
+        const int pos = sl->first + a, n_atoms = sl->n_atoms;
+        const bool mine = pos >= args.shard_begin && pos < args.shard_end;
+
+        // ---- gather: the only use of the tile ----------------------------------------------------------------
+        Self me;
+        int nn = 0;
+        if (mine) {
+            if (sl->staged) {
+                const int self_idx = sl->self_off + pos;
+                me = load_self(tile[self_idx]);
+                if (ALG == 0) {
+                    nn = gather_run<ALG, T>(tile, sl->total, self_idx, 0, me, wm.recs, wm.cidx, 0, kNbCap, lane);
+                } else {  // S&R keeps GLOBAL candidate positions (its exact re-check outlives the tile)
                     for (int r = 0; r < 9; ++r)
-                        nn = gather_run<ALG, T>(ws.atoms + sl->begin[r], sl->count[r], r == 4 ? pos - sl->begin[4] : -1, sl->begin[r], me,
+                        nn = gather_run<ALG, T>(tile + sl->off[r], sl->count[r], r == 4 ? pos - sl->begin[4] : -1, sl->begin[r], me,
                                                 wm.recs, wm.cidx, nn, kNbCap, lane);
-                    finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane);
                 }
-                __syncwarp();
+            } else {  // oversized neighbourhood: read the candidates straight from global memory
+                me = load_self(ws.atoms[pos]);
+                for (int r = 0; r < 9; ++r)
+                    nn = gather_run<ALG, T>(ws.atoms + sl->begin[r], sl->count[r], r == 4 ? pos - sl->begin[4] : -1, sl->begin[r], me,
+                                            wm.recs, wm.cidx, nn, kNbCap, lane);
             }
-        } else {
-            ++dead;
         }
         __syncwarp();
-        int d = 0;
+        int g = 0;
         if (lane == 0) {
             __threadfence_block();
-            d = atomicAdd(&sl->done, 1);
+            g = atomicAdd(&sl->gathered, 1) + 1;
         }
-        d = __shfl_sync(kFull, d, 0);
-        if (dead == kRingSlots) break;                     // a full turn of empty slots: the queue is drained
-        if (d == kWarpsPerCta - 1) fill_slot(ws, args, n_items, sl, tile, &full[s], lane);
+        g = __shfl_sync(kFull, g, 0);
+        if (g == n_atoms) fill_slot(ws, args, n_items, sl, tile, &full[s], f + kRingSlots, lane);  // last gather: recycle the slot
+
+        // ---- integrate (no shared state besides the warp's own lists) -----------------------------------------
+        if (mine) finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane);
+        __syncwarp();
     }
 }
 
