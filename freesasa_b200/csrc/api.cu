@@ -232,6 +232,10 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
         g_launches += launches;
         return fail("non-finite coordinate or radius in input");
     }
+    if (c->h_status[kCtrStalled]) {
+        g_launches += launches;
+        return fail("internal error: the integration kernel's tile ring stalled (results discarded)");
+    }
     float overflow_ms = 0.f;
     cudaEventElapsedTime(&s.device_ms, c->ev[0], c->ev[2]);
     cudaEventElapsedTime(&s.integrate_ms, c->ev[1], c->ev[2]);

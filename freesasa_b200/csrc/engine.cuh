@@ -57,6 +57,7 @@ enum CounterSlot {
     kCtrMaxCand = 3,    // max candidate count among overflow atoms
     kCtrBadInput = 4,   // non-finite coordinate or radius seen
     kCtrQueue2 = 5,     // queue head of the overflow kernel
+    kCtrStalled = 6,    // a warp gave up waiting for a tile (internal error, reported to the host)
     kCtrCount = 16
 };
 

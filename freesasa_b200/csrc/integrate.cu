@@ -43,17 +43,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// Waits for the phase with the given parity.  Returns false instead of spinning forever (a stalled ring is
+// reported to the host as an error, it must never hang the GPU).
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
     const uint32_t addr = smem_addr(bar);
-    do {
+    long long t0 = 0;
+    for (int spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
+        if (done) return true;
+        if ((spin & 1023) == 1023) {                       // ~2 s at 2 GHz: far beyond any legitimate wait
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) return false;
+        }
+    }
 }
 // global -> shared bulk copy (TMA, 1-D); bytes must be a multiple of 16, both addresses 16-B aligned
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
@@ -827,9 +836,10 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     if (warp == 0)
         for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], s, lane);
 
+    int retries = 0;
     for (;;) {
         // ---- claim one atom (lane 0 negotiates, the warp follows) ----------------------------------------
-        int code = 0, f = 0, a = 0;                        // code 0: look again, 1: atom claimed, 2: all work done
+        int code = 0, f = 0, a = 0;                        // code 0: look again, 1: atom claimed, 2: all work done, 3: stalled
         if (lane == 0) {
             f = ld_volatile(&cur);
             Slot *sl = &slots[f % kRingSlots];
@@ -839,18 +849,32 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
                 if (all) code = 2;
                 else atomicCAS(&cur, f, f + 1);
             } else {
-                mbar_wait(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u);
-                const int w = ld_volatile(&sl->claim);
-                if (((unsigned)w >> 16) == (unsigned)(f & 0xffff)) {
-                    a = w & 0xffff;
-                    if (a >= ld_volatile(&sl->n_atoms)) atomicCAS(&cur, f, f + 1);         // fill exhausted: open the next one
-                    else if (atomicCAS(&sl->claim, w, w + 1) == w) code = 1;
+                if (!mbar_wait(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u)) {
+                    atomicExch(ws.counters + kCtrStalled, 1);
+                    code = 3;
+                } else {
+                    const int w = ld_volatile(&sl->claim);
+                    const unsigned gen = (unsigned)w >> 16;
+                    if (gen == (unsigned)(f & 0xffff)) {
+                        a = w & 0xffff;
+                        if (a >= ld_volatile(&sl->n_atoms)) atomicCAS(&cur, f, f + 1);     // fill exhausted: open the next one
+                        else if (atomicCAS(&sl->claim, w, w + 1) == w) code = 1;
+                    } else if (((gen - (unsigned)f) & 0xffffu) < 0x8000u) {
+                        atomicCAS(&cur, f, f + 1);         // the slot already hosts a later fill: fill f is history
+                    }
                 }
             }
         }
         code = __shfl_sync(kFull, code, 0);
-        if (code == 2) break;
-        if (code == 0) continue;
+        if (code >= 2) break;
+        if (code == 0) {
+            if (++retries > (1 << 26)) {                   // livelock guard: report instead of hanging the GPU
+                if (lane == 0) atomicExch(ws.counters + kCtrStalled, 1);
+                break;
+            }
+            continue;
+        }
+        retries = 0;
         f = __shfl_sync(kFull, f, 0);
         a = __shfl_sync(kFull, a, 0);
         const int s = f % kRingSlots;
