@@ -64,6 +64,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
         }
     }
 }
+// one non-blocking probe of the phase with the given parity
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 // global -> shared bulk copy (TMA, 1-D); bytes must be a multiple of 16, both addresses 16-B aligned
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
@@ -836,9 +847,13 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     if (warp == 0)
         for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], s, lane);
 
-    int retries = 0;
+    long long wait_since = 0;
     for (;;) {
         // ---- claim one atom (lane 0 negotiates, the warp follows) ----------------------------------------
+        // The slot's claim word names the fill it hosts.  Only when that is the fill `cur` points at do we
+        // look at the mbarrier (whose parity is only meaningful for the phase of the hosted fill); a slot
+        // that already hosts a LATER fill means fill `cur` is history (its last gather recycled the slot
+        // before anybody noticed it was exhausted), an EARLIER one means the refill is still to come.
         int code = 0, f = 0, a = 0;                        // code 0: look again, 1: atom claimed, 2: all work done, 3: stalled
         if (lane == 0) {
             f = ld_volatile(&cur);
@@ -849,38 +864,39 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
                 if (all) code = 2;
                 else atomicCAS(&cur, f, f + 1);
             } else {
-                if (!mbar_wait(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u)) {
-                    atomicExch(ws.counters + kCtrStalled, 1);
-                    code = 3;
-                } else {
-                    const int w = ld_volatile(&sl->claim);
-                    const unsigned gen = (unsigned)w >> 16;
-                    if (gen == (unsigned)(f & 0xffff)) {
+                const int w = ld_volatile(&sl->claim);
+                const unsigned gen = (unsigned)w >> 16;
+                if (gen == (unsigned)(f & 0xffff)) {
+                    if (mbar_test(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u)) {
                         a = w & 0xffff;
                         if (a >= ld_volatile(&sl->n_atoms)) atomicCAS(&cur, f, f + 1);     // fill exhausted: open the next one
                         else if (atomicCAS(&sl->claim, w, w + 1) == w) code = 1;
-                    } else if (((gen - (unsigned)f) & 0xffffu) < 0x8000u) {
-                        atomicCAS(&cur, f, f + 1);         // the slot already hosts a later fill: fill f is history
                     }
+                } else if (((gen - (unsigned)f) & 0xffffu) < 0x8000u) {
+                    atomicCAS(&cur, f, f + 1);
                 }
+            }
+            if (code == 0) {                               // nothing to do right now: back off, but never hang
+                const long long now = clock64();
+                if (wait_since == 0) wait_since = now;
+                else if (now - wait_since > 4000000000ll) {
+                    atomicExch(ws.counters + kCtrStalled, 1);
+                    code = 3;
+                }
+                __nanosleep(64);
+            } else {
+                wait_since = 0;
             }
         }
         code = __shfl_sync(kFull, code, 0);
         if (code >= 2) break;
-        if (code == 0) {
-            if (++retries > (1 << 26)) {                   // livelock guard: report instead of hanging the GPU
-                if (lane == 0) atomicExch(ws.counters + kCtrStalled, 1);
-                break;
-            }
-            continue;
-        }
-        retries = 0;
+        if (code == 0) continue;
         f = __shfl_sync(kFull, f, 0);
         a = __shfl_sync(kFull, a, 0);
         const int s = f % kRingSlots;
         Slot *sl = &slots[s];
         double4 *tile = tiles + (size_t)s * kTileCap;
-        mbar_wait(&full[s], (uint32_t)(f / kRingSlots) & 1u);     // every lane observes the completed phase (immediate)
+        mbar_wait(&full[s], (uint32_t)(f / kRingSlots) & 1u);     // every lane observes the completed phase (returns at once)
         const int pos = sl->first + a, n_atoms = sl->n_atoms;
         const bool mine = pos >= args.shard_begin && pos < args.shard_end;
 
