@@ -234,7 +234,10 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     }
     if (c->h_status[kCtrStalled]) {
         g_launches += launches;
-        return fail("internal error: the integration kernel's tile ring stalled (results discarded)");
+        const int *d = c->h_status + 7;
+        return fail("internal error: the integration kernel's tile ring stalled (results discarded) "
+                    "[cur %d | slot0 claim %08x gathered %d n*2+dead %d | slot1 claim %08x gathered %d n*2+dead %d | bars %d | queue %d of %d]",
+                    d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], c->h_status[kCtrItems]);
     }
     float overflow_ms = 0.f;
     cudaEventElapsedTime(&s.device_ms, c->ev[0], c->ev[2]);

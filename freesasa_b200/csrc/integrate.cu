@@ -840,6 +840,9 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         cur = 0;
         for (int s = 0; s < kRingSlots; ++s) {
             slots[s].dead = 0;
+            slots[s].n_atoms = 0;
+            slots[s].gathered = 0;
+            slots[s].claim = ((s - kRingSlots) & 0xffff) << 16;   // "one fill older than the first": not ready yet
             mbar_init(&full[s], 1);
         }
     }
@@ -880,7 +883,14 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
                 const long long now = clock64();
                 if (wait_since == 0) wait_since = now;
                 else if (now - wait_since > 4000000000ll) {
-                    atomicExch(ws.counters + kCtrStalled, 1);
+                    if (atomicExch(ws.counters + kCtrStalled, 1) == 0) {   // first reporter leaves a post-mortem
+                        int *dbg = ws.counters + 7;
+                        dbg[0] = f;
+                        dbg[1] = slots[0].claim; dbg[2] = slots[0].gathered; dbg[3] = slots[0].n_atoms * 2 + slots[0].dead;
+                        dbg[4] = slots[1].claim; dbg[5] = slots[1].gathered; dbg[6] = slots[1].n_atoms * 2 + slots[1].dead;
+                        dbg[7] = (int)mbar_test(&full[0], 0) + 2 * (int)mbar_test(&full[0], 1) + 4 * (int)mbar_test(&full[1], 0) + 8 * (int)mbar_test(&full[1], 1);
+                        dbg[8] = ld_volatile(ws.counters + kCtrQueue);
+                    }
                     code = 3;
                 }
                 __nanosleep(64);
