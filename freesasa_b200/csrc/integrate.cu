@@ -612,7 +612,7 @@ __device__ __forceinline__ bool sr_exact_hidden(const double *pd, int q, const S
 }
 
 template <typename T>
-__device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, const double4 *cand_base, int nn,
+__device__ __forceinline__ double sr_atom(Rec4<T> *recs, int *cidx, const double4 *cand_base, int nn,
                                           const Self &s, int npts, const float4 *pf, const double *pd, int lane)
 {
     int exposed = 0;
@@ -627,18 +627,52 @@ __device__ __forceinline__ double sr_atom(const Rec4<T> *recs, const int *cidx, 
             exposed += __popc(__ballot_sync(kFull, !bur));
         }
     } else {
+        // fp32 production path.  The test points arrive PATCH-ORDERED from the host (32 consecutive
+        // points form a compact patch of the sphere; the count does not depend on the order), so a
+        // round of 32 lanes is usually hidden by one or two neighbours and leaves the loop early.
+        // Neighbours are tested four at a time with one vote per block; the block that finished a
+        // round is where the next (adjacent) patch starts — the warp-wide version of the reference's
+        // "begin with the neighbour that hid the previous point" (src/sasa_sr.c:305-328).
         const float band = sr_band<T>(recs, nn, lane);
+        const int nn4 = (nn + 3) & ~3;
+        if (lane < nn4 - nn) {                             // pad with neighbours that hide nothing
+            Rec4<T> pad;
+            pad.a = 0; pad.b = 0; pad.c = 0; pad.d = (T)3.0e38f;
+            recs[nn + lane] = pad;
+            cidx[nn + lane] = 0;
+        }
+        __syncwarp();
+        int k_start = 0;
         for (int q0 = 0; q0 < npts; q0 += 32) {
             const int q = q0 + lane;
             const bool active = q < npts;
             const float4 u = active ? pf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             bool bur = !active;
-            for (int k = 0; k < nn; ++k) {
-                const Rec4<T> r = recs[k];                 // warp-uniform address: shared-memory broadcast
-                const float diff = fmaf(u.x, (float)r.a, fmaf(u.y, (float)r.b, u.z * (float)r.c)) - (float)r.d;
-                if (diff > band) bur = true;
-                else if (diff >= -band && !bur) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[k]]);
-                if (__all_sync(kFull, bur)) break;
+            int kb = k_start;
+            for (int done = 0; done < nn4; done += 4) {
+                const Rec4<T> r0 = recs[kb], r1 = recs[kb + 1], r2 = recs[kb + 2], r3 = recs[kb + 3];   // broadcast
+                const float d0 = fmaf(u.x, (float)r0.a, fmaf(u.y, (float)r0.b, u.z * (float)r0.c)) - (float)r0.d;
+                const float d1 = fmaf(u.x, (float)r1.a, fmaf(u.y, (float)r1.b, u.z * (float)r1.c)) - (float)r1.d;
+                const float d2 = fmaf(u.x, (float)r2.a, fmaf(u.y, (float)r2.b, u.z * (float)r2.c)) - (float)r2.d;
+                const float d3 = fmaf(u.x, (float)r3.a, fmaf(u.y, (float)r3.b, u.z * (float)r3.c)) - (float)r3.d;
+                const float dmax = fmaxf(fmaxf(d0, d1), fmaxf(d2, d3));
+                if (dmax > band) bur = true;
+                // anything within the rounding band of its threshold is re-decided exactly (rare)
+                const bool amb = !bur && dmax >= -band;
+                if (__any_sync(kFull, amb)) {
+                    if (amb) {
+                        if (fabsf(d0) <= band) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[kb]]);
+                        if (!bur && fabsf(d1) <= band) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[kb + 1]]);
+                        if (!bur && fabsf(d2) <= band) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[kb + 2]]);
+                        if (!bur && fabsf(d3) <= band) bur = sr_exact_hidden(pd, q, s, cand_base[cidx[kb + 3]]);
+                    }
+                }
+                if (__all_sync(kFull, bur)) {
+                    k_start = kb;
+                    break;
+                }
+                kb += 4;
+                if (kb >= nn4) kb = 0;
             }
             exposed += __popc(__ballot_sync(kFull, !bur));
         }
