@@ -38,6 +38,11 @@ N_ATOMS = 100_000
 N_SLICES = 100
 PROBE = 1.4
 ALG_BYTES_PER_ATOM = 40.0
+# DRAM traffic of the dominant kernel, from the committed ncu --set full capture of this same command
+# (bench.py --steps 2 --warmup 3): 3.87 MB read + 0 B written per launch for 100k atoms = 38.7 B/atom,
+# i.e. the 32 B/atom sorted double4 records are fetched once and everything else stays in L2/shared memory.
+NCU_DRAM_BYTES_PER_LAUNCH = 3867904
+NCU_SOURCE = "profiles/r1_06_lr_ring_v2.txt"
 METRIC = "atoms/sec (LR n_slices=100)"
 WORKLOAD = "C2: 100k-atom synthetic globular coord array, Lee-Richards n_slices=100, probe 1.4 A"
 
@@ -279,7 +284,9 @@ def main():
                     else "pinned host -> H2D -> calc_device -> NCCL all-gather -> D2H on every rank"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_integrate<LR,float>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, " + NCU_SOURCE + ")",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_ATOM * N_ATOMS, "peak_source": peak_src,
                          "algorithmic_bytes_per_atom": ALG_BYTES_PER_ATOM, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (total_ms / args.steps),
                          "note": "FP32-issue bound kernel; HBM fraction is tiny by construction (DESIGN.md)"},

@@ -104,8 +104,8 @@ template <> struct Consts<double> {
 };
 
 // arcs one slice can produce: every neighbour (+4 sentinels) in the general paths, at most
-// 64 + 32 synthetic + 4 sentinels in the <= 64-neighbour path
-__host__ __device__ constexpr int arc_cap(int cap) { return cap + 4 > 100 ? cap + 4 : 100; }
+// 96 + 32 synthetic + 4 sentinels in the <= 96-neighbour path
+__host__ __device__ constexpr int arc_cap(int cap) { return cap + 4 > 132 ? cap + 4 : 132; }
 
 template <int ALG, typename T> struct WarpLayout {
     // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
@@ -410,7 +410,7 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
     return delta * Ri_d * acc;
 }
 
-// ---- step 2c: the common case, at most 64 neighbours ------------------------------------------------
+// ---- step 2c: the common case, at most 96 neighbours (K = 1, 2 or 3 records per lane) -----------------
 // The (z-sorted) records live in REGISTERS, two per lane, for all slices of the atom.  Per slice:
 //   1. both halves evaluate their circle-circle configuration; a half whose neighbours are all out of
 //      z-range is skipped (the records are z-sorted, so low slices skip the upper half and vice versa);
@@ -424,13 +424,14 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
 // Exactness: a sector counts as covered only if ONE arc contains it entirely (integer sector borders are
 // exact in fp32), so replacing the arcs inside covered sectors by the sectors themselves does not change
 // the union.
-__device__ __forceinline__ void lr_prepare_sorted64(Rec4<float> *recs, int nn, int lane)
+template <int K>
+__device__ __forceinline__ void lr_prepare_sorted(Rec4<float> *recs, int nn, int lane)
 {
     const float kS = 5.092958178940651f;                   // sectors per radian
-    Rec4<float> o[2];
-    int rank[2];
+    Rec4<float> o[K];
+    int rank[K];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < K; ++h) {
         const int j = lane + 32 * h;
         rank[h] = -1;
         if (j < nn) {
@@ -449,7 +450,7 @@ __device__ __forceinline__ void lr_prepare_sorted64(Rec4<float> *recs, int nn, i
     }
     __syncwarp();
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < K; ++h)
         if (rank[h] >= 0) recs[rank[h]] = o[h];
     __syncwarp();
 }
@@ -503,16 +504,20 @@ __device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
     return (h.has && cnt > 0) ? mask : 0u;
 }
 
-__device__ __forceinline__ double lr_atom_fast64(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
-                                                 double Ri_d, int ns, int lane)
+template <int K>
+__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
+                                                double Ri_d, int ns, int lane)
 {
     const float Ri = (float)Ri_d;
     const double delta = 2.0 * Ri_d / ns;
     const unsigned lt = lanemask_lt();
-    const bool v0 = lane < nn, v1 = lane + 32 < nn;
-    const bool two_halves = nn > 32;
-    const Rec4<float> r0 = recs[v0 ? lane : 0];
-    const Rec4<float> r1 = recs[v1 ? lane + 32 : 0];
+    Rec4<float> r[K];                                      // this lane's K records, for all slices of the atom
+    bool v[K];
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+        v[h] = lane + 32 * h < nn;
+        r[h] = recs[v[h] ? lane + 32 * h : 0];
+    }
     double acc = 0.0;                                      // exposed angle in sectors
 
     for (int s = 0; s < ns; ++s) {
@@ -521,57 +526,65 @@ __device__ __forceinline__ double lr_atom_fast64(const Rec4<float> *recs, KeyArc
         const float a2 = (Ri - az) * (Ri + az);
         if (!(a2 > 0.f)) continue;
         const float a = fast_sqrt(a2);
-        HalfArc h0 = half_eval(r0, v0, zr, a);
-        HalfArc h1;
-        h1.st = 0.f; h1.en = 0.f; h1.has = false; h1.bur = false;
-        if (two_halves) h1 = half_eval(r1, v1, zr, a);
-        if (__any_sync(kFull, h0.bur || h1.bur)) continue;                 // buried slice
-        const unsigned any0 = __ballot_sync(kFull, h0.has), any1 = __ballot_sync(kFull, h1.has);
-        if ((any0 | any1) == 0u) {                                         // free circle
+        HalfArc h[K];
+        bool bur = false;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            h[i].st = 0.f; h[i].en = 0.f; h[i].has = false; h[i].bur = false;
+            if (i == 0 || nn > 32 * i) h[i] = half_eval(r[i], v[i], zr, a);
+            bur = bur || h[i].bur;
+        }
+        if (__any_sync(kFull, bur)) continue;                              // buried slice
+        unsigned any[K], any_all = 0u;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            any[i] = __ballot_sync(kFull, h[i].has);
+            any_all |= any[i];
+        }
+        if (any_all == 0u) {                                               // free circle
             if (lane == 0) acc += 32.0;
             continue;
         }
         unsigned mask = 0u;
-        if (any0) mask |= half_finish(h0, r0.d);
-        if (any1) mask |= half_finish(h1, r1.d);
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+            if (any[i]) mask |= half_finish(h[i], r[i].d);
         const unsigned full = __reduce_or_sync(kFull, mask);
         if (full == 0xffffffffu) continue;                                 // every sector inside some arc
         // arcs with an end in an uncovered sector, plus one synthetic arc per run of covered sectors
-        const bool rel0 = h0.has && (!((full >> ((int)h0.st & 31)) & 1u) || !((full >> ((int)h0.en & 31)) & 1u));
-        const bool rel1 = h1.has && (!((full >> ((int)h1.st & 31)) & 1u) || !((full >> ((int)h1.en & 31)) & 1u));
-        const bool syn = ((full >> lane) & 1u) && !((full >> ((lane + 31) & 31)) & 1u);
-        const unsigned b0 = __ballot_sync(kFull, rel0), b1 = __ballot_sync(kFull, rel1), b2 = __ballot_sync(kFull, syn);
-        const int n0 = __popc(b0), n1 = __popc(b1), narc = n0 + n1 + __popc(b2);
+        int narc = 0;
         float my_max = 0.f;
-        if (rel0) {
-            const int slot = __popc(b0 & lt);
-            KeyArc arc;
-            arc.key = (__float_as_int(h0.st) & ~0xff) | slot;
-            arc.en = h0.en;
-            arcs[slot] = arc;
-            starts[slot] = h0.st;
-            my_max = h0.en;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const bool rel = h[i].has && (!((full >> ((int)h[i].st & 31)) & 1u) || !((full >> ((int)h[i].en & 31)) & 1u));
+            const unsigned b = __ballot_sync(kFull, rel);
+            if (rel) {
+                const int slot = narc + __popc(b & lt);
+                KeyArc arc;
+                arc.key = (__float_as_int(h[i].st) & ~0xff) | slot;
+                arc.en = h[i].en;
+                arcs[slot] = arc;
+                starts[slot] = h[i].st;
+                my_max = fmaxf(my_max, h[i].en);
+            }
+            narc += __popc(b);
         }
-        if (rel1) {
-            const int slot = n0 + __popc(b1 & lt);
-            KeyArc arc;
-            arc.key = (__float_as_int(h1.st) & ~0xff) | slot;
-            arc.en = h1.en;
-            arcs[slot] = arc;
-            starts[slot] = h1.st;
-            my_max = fmaxf(my_max, h1.en);
-        }
-        if (syn) {
-            const unsigned rot = __funnelshift_r(full, full, lane);        // covered run starts at bit 0
-            const int ones = __ffs(~rot) - 1;                              // full != all ones here
-            const int slot = n0 + n1 + __popc(b2 & lt);
-            const float st = (float)lane, en = (float)(lane + ones);
-            KeyArc arc;
-            arc.key = (__float_as_int(st) & ~0xff) | slot;
-            arc.en = en;
-            arcs[slot] = arc;
-            starts[slot] = st;
-            my_max = fmaxf(my_max, en);
+        {
+            const bool syn = ((full >> lane) & 1u) && !((full >> ((lane + 31) & 31)) & 1u);
+            const unsigned b = __ballot_sync(kFull, syn);
+            if (syn) {
+                const unsigned rot = __funnelshift_r(full, full, lane);    // covered run starts at bit 0
+                const int ones = __ffs(~rot) - 1;                          // full != all ones here
+                const int slot = narc + __popc(b & lt);
+                const float st = (float)lane, en = (float)(lane + ones);
+                KeyArc arc;
+                arc.key = (__float_as_int(st) & ~0xff) | slot;
+                arc.en = en;
+                arcs[slot] = arc;
+                starts[slot] = st;
+                my_max = fmaxf(my_max, en);
+            }
+            narc += __popc(b);
         }
         my_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(my_max)));
         acc += (double)merge_keyed(arcs, starts, narc, fmaxf(my_max - 32.f, 0.f), lane);
@@ -716,9 +729,9 @@ __device__ __forceinline__ void finish_atom(const Workspace &ws, const Integrate
                 Rec4<float> *recs = reinterpret_cast<Rec4<float> *>(wm.recs);
                 KeyArc *arcs = reinterpret_cast<KeyArc *>(wm.arcs);
                 float *starts = reinterpret_cast<float *>(wm.starts);
-                if (nn <= 64) {
-                    lr_prepare_sorted64(recs, nn, lane);
-                    area = lr_atom_fast64(recs, arcs, starts, nn, s.R, args.resolution, lane);
+                if (nn <= 96) {                            // ONE instantiation (K = 3) for all of them: the kernel is
+                    lr_prepare_sorted<3>(recs, nn, lane);  // instruction-cache sensitive (ncu: no_instruction stalls
+                    area = lr_atom_fastk<3>(recs, arcs, starts, nn, s.R, args.resolution, lane);  // with K = 1, 2, 3 side by side)
                 } else {
                     lr_prepare<float>(recs, nn, lane);
                     area = lr_atom_fast(recs, arcs, starts, nn, s.R, args.resolution, lane);
