@@ -199,7 +199,8 @@ def main():
     h_all = torch.empty(world * N_ATOMS, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     eng = fs.Engine(local_rank, fs.FP32)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # a real (non-legacy) stream: the engine replays its launch sequence as a CUDA graph on it
+    torch.cuda.set_stream(stream)
 
     def device_step():
         eng.calc_device(fs.LEE_RICHARDS, d_xyz, d_rad, PROBE, N_SLICES, out=d_out)

@@ -69,6 +69,14 @@ struct fsb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int *h_status = nullptr;  // pinned, kCtrCount ints
+    // The fixed launch sequence of a call (3 memsets, 10 kernels, 3 event records, the status read-back) is
+    // captured once per distinct (Workspace, IntegrateArgs) pair and replayed as ONE CUDA graph launch: the
+    // device timeline no longer depends on how fast the host can issue 17 calls (matters for small structures
+    // and on a busy host).
+    cudaGraphExec_t graph_exec = nullptr;
+    Workspace graph_ws;
+    IntegrateArgs graph_ia;
+    int graph_launches = 0;
     unsigned char *h_stage = nullptr;  // pinned staging for host-pointer calls: inputs then outputs
     size_t h_stage_cap = 0;
     int grid_ctas[2][2] = {{0, 0}, {0, 0}};
@@ -240,6 +248,8 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     if (rq.shard_count < 1 || rq.shard_index < 0 || rq.shard_index >= rq.shard_count) return fail("invalid shard %d of %d", rq.shard_index, rq.shard_count);
     cudaStream_t st = rq.stream;
     Workspace ws;
+    std::memset(&ws, 0, sizeof ws);  // the struct doubles as the graph cache key: no indeterminate padding
+    ws.n_struct = 1;
     if (ensure_workspace(c, rq.n, rq.n_struct, ws)) return FSB200_FAIL;
     ws.xyz = rq.d_xyz;
     ws.radii = rq.d_radii;
@@ -247,7 +257,8 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     if (rq.n_struct > 1)
         CU(cudaMemcpyAsync(ws.offsets, rq.h_offsets, sizeof(int) * ((size_t)rq.n_struct + 1), cudaMemcpyHostToDevice, st));
 
-    IntegrateArgs ia{};
+    IntegrateArgs ia;
+    std::memset(&ia, 0, sizeof ia);
     ia.alg = rq.alg;
     ia.resolution = rq.resolution;
     ia.precision = c->precision;
@@ -266,12 +277,41 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     ia.grid_ctas = ctas;
 
     int launches = 0;
-    CU(cudaEventRecord(c->ev[0], st));
-    launches += launch_cell_build(ws, st);
-    CU(cudaEventRecord(c->ev[1], st));
-    launches += launch_integrate(ws, ia, st);
-    CU(cudaEventRecord(c->ev[2], st));
-    CU(cudaMemcpyAsync(c->h_status, ws.counters, sizeof(int) * kCtrCount, cudaMemcpyDeviceToHost, st));
+    auto enqueue = [&](cudaStream_t s) -> int {
+        int k = 0;
+        CU(cudaEventRecord(c->ev[0], s));
+        k += launch_cell_build(ws, s);
+        CU(cudaEventRecord(c->ev[1], s));
+        k += launch_integrate(ws, ia, s);
+        CU(cudaEventRecord(c->ev[2], s));
+        CU(cudaMemcpyAsync(c->h_status, ws.counters, sizeof(int) * kCtrCount, cudaMemcpyDeviceToHost, s));
+        launches = k;
+        return FSB200_SUCCESS;
+    };
+    bool replayed = false;
+    if (c->graph_exec && std::memcmp(&c->graph_ws, &ws, sizeof ws) == 0 && std::memcmp(&c->graph_ia, &ia, sizeof ia) == 0) {
+        replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
+        launches = c->graph_launches;
+    } else if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+               cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+        c->graph_exec = nullptr;
+        const int rc_enq = enqueue(st);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+        if (rc_enq == FSB200_SUCCESS && e_end == cudaSuccess && graph &&
+            cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess) {
+            c->graph_ws = ws;
+            c->graph_ia = ia;
+            c->graph_launches = launches;
+            replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
+        } else {
+            c->graph_exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+    }
+    if (!replayed && enqueue(st)) return FSB200_FAIL;  // plain stream launches (legacy stream, or capture refused)
     if (after_enqueue(st)) return FSB200_FAIL;
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
@@ -295,8 +335,9 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
                     d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], c->h_status[kCtrItems]);
     }
     float overflow_ms = 0.f;
-    cudaEventElapsedTime(&s.device_ms, c->ev[0], c->ev[2]);
-    cudaEventElapsedTime(&s.integrate_ms, c->ev[1], c->ev[2]);
+    if (cudaEventElapsedTime(&s.device_ms, c->ev[0], c->ev[2]) != cudaSuccess) s.device_ms = -1.f;
+    if (cudaEventElapsedTime(&s.integrate_ms, c->ev[1], c->ev[2]) != cudaSuccess) s.integrate_ms = -1.f;
+    cudaGetLastError();
     if (s.n_overflow > 0) {
         // Large neighbourhoods (more than kNbCap neighbours): second pass with the lists in global memory.
         const int cap = ((c->h_status[kCtrMaxCand] + 7) / 8) * 8;
@@ -439,6 +480,7 @@ void fsb200_ctx_destroy(fsb200_ctx *c)
     c->items.release(); c->scratch.release(); c->points_f.release(); c->points_d.release();
     for (int k = 0; k < 4; ++k)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
