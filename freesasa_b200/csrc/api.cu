@@ -69,13 +69,11 @@ struct fsb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int *h_status = nullptr;  // pinned, kCtrCount ints
-    // The fixed launch sequence of a call (3 memsets, 10 kernels, 3 event records, the status read-back) is
-    // captured once per distinct (Workspace, IntegrateArgs) pair and replayed as ONE CUDA graph launch: the
-    // device timeline no longer depends on how fast the host can issue 17 calls (matters for small structures
-    // and on a busy host).
+    // The cell-list build (3 memsets + 9 kernels) is captured once per distinct Workspace and replayed as ONE
+    // CUDA graph launch: the device timeline no longer depends on how fast the host can issue 12 calls
+    // (matters for small structures and on a busy host).
     cudaGraphExec_t graph_exec = nullptr;
     Workspace graph_ws;
-    IntegrateArgs graph_ia;
     int graph_launches = 0;
     unsigned char *h_stage = nullptr;  // pinned staging for host-pointer calls: inputs then outputs
     size_t h_stage_cap = 0;
@@ -276,33 +274,24 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     if (ctas == 0) ctas = integrate_grid_ctas(rq.alg, c->precision, c->device);
     ia.grid_ctas = ctas;
 
+    // Cell-list build: 3 memsets + 9 small kernels whose arguments depend only on the workspace -> captured
+    // once per distinct Workspace and replayed as ONE graph launch.  The integration kernel is launched
+    // directly so that plain CUDA events can bracket it (events recorded inside a graph cannot be timed).
     int launches = 0;
-    auto enqueue = [&](cudaStream_t s) -> int {
-        int k = 0;
-        CU(cudaEventRecord(c->ev[0], s));
-        k += launch_cell_build(ws, s);
-        CU(cudaEventRecord(c->ev[1], s));
-        k += launch_integrate(ws, ia, s);
-        CU(cudaEventRecord(c->ev[2], s));
-        CU(cudaMemcpyAsync(c->h_status, ws.counters, sizeof(int) * kCtrCount, cudaMemcpyDeviceToHost, s));
-        launches = k;
-        return FSB200_SUCCESS;
-    };
+    CU(cudaEventRecord(c->ev[0], st));
     bool replayed = false;
-    if (c->graph_exec && std::memcmp(&c->graph_ws, &ws, sizeof ws) == 0 && std::memcmp(&c->graph_ia, &ia, sizeof ia) == 0) {
+    if (c->graph_exec && std::memcmp(&c->graph_ws, &ws, sizeof ws) == 0) {
         replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
         launches = c->graph_launches;
     } else if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
                cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
         if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
         c->graph_exec = nullptr;
-        const int rc_enq = enqueue(st);
+        launches = launch_cell_build(ws, st);
         cudaGraph_t graph = nullptr;
         const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
-        if (rc_enq == FSB200_SUCCESS && e_end == cudaSuccess && graph &&
-            cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess) {
+        if (e_end == cudaSuccess && graph && cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess) {
             c->graph_ws = ws;
-            c->graph_ia = ia;
             c->graph_launches = launches;
             replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
         } else {
@@ -311,7 +300,11 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
     }
-    if (!replayed && enqueue(st)) return FSB200_FAIL;  // plain stream launches (legacy stream, or capture refused)
+    if (!replayed) launches = launch_cell_build(ws, st);  // plain stream launches (legacy stream, or capture refused)
+    CU(cudaEventRecord(c->ev[1], st));
+    launches += launch_integrate(ws, ia, st);
+    CU(cudaEventRecord(c->ev[2], st));
+    CU(cudaMemcpyAsync(c->h_status, ws.counters, sizeof(int) * kCtrCount, cudaMemcpyDeviceToHost, st));
     if (after_enqueue(st)) return FSB200_FAIL;
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
