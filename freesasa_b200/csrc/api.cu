@@ -73,7 +73,7 @@ struct fsb200_ctx {
     // CUDA graph launch: the device timeline no longer depends on how fast the host can issue 12 calls
     // (matters for small structures and on a busy host).
     cudaGraphExec_t graph_exec = nullptr;
-    Workspace graph_ws;
+    Workspace graph_ws, last_ws;
     int graph_launches = 0;
     unsigned char *h_stage = nullptr;  // pinned staging for host-pointer calls: inputs then outputs
     size_t h_stage_cap = 0;
@@ -283,10 +283,11 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     if (c->graph_exec && std::memcmp(&c->graph_ws, &ws, sizeof ws) == 0) {
         replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
         launches = c->graph_launches;
+    } else if (std::memcmp(&c->last_ws, &ws, sizeof ws) != 0) {
+        // first sighting of this workspace: plain launches; capturing pays off only for repeated shapes
     } else if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+               (c->graph_exec ? (cudaGraphExecDestroy(c->graph_exec), c->graph_exec = nullptr, true) : true) &&
                cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-        c->graph_exec = nullptr;
         launches = launch_cell_build(ws, st);
         cudaGraph_t graph = nullptr;
         const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
@@ -300,7 +301,8 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
     }
-    if (!replayed) launches = launch_cell_build(ws, st);  // plain stream launches (legacy stream, or capture refused)
+    if (!replayed) launches = launch_cell_build(ws, st);  // plain stream launches (new shape, legacy stream, or capture refused)
+    c->last_ws = ws;
     CU(cudaEventRecord(c->ev[1], st));
     launches += launch_integrate(ws, ia, st);
     CU(cudaEventRecord(c->ev[2], st));
