@@ -154,6 +154,37 @@ def test_edge_cases(eng32, eng64):
         assert maxerr(eng64.calc(0, x, r, 1.4, 25), ob.oracle_calc(x, r, 0, 1.4, 25)) < LR_TOL_FP64, name
 
 
+@pytest.mark.parametrize("res", [1, 2, 3, 7, 31, 32, 33, 257])
+def test_odd_resolutions(eng32, eng64, res):
+    """Resolutions that are not multiples of the warp width, down to a single slice / test point."""
+    x, r = fs.workloads.globule(600, seed=8)
+    assert maxerr(eng32.calc(0, x, r, 1.4, res), ob.oracle_calc(x, r, 0, 1.4, res)) < 2e-3 / max(1, min(res, 4)) + LR_TOL_FP32
+    assert maxerr(eng64.calc(0, x, r, 1.4, res), ob.oracle_calc(x, r, 0, 1.4, res)) < LR_TOL_FP64
+    assert maxerr(eng32.calc(1, x, r, 1.4, res), ob.oracle_calc(x, r, 1, 1.4, res)) < SR_TOL
+
+
+def test_ragged_batch_with_tiny_structures(eng32):
+    """A batch mixing 1-atom, 2-atom and ordinary structures (ragged sizes, cells with a single atom)."""
+    rng = np.random.default_rng(12)
+    structs = [(np.zeros((1, 3)), np.array([1.7])),
+               (np.array([[0.0, 0, 0], [1.0, 0.5, 0.2]]) + 300.0, np.array([1.5, 1.9])),
+               fs.workloads.globule(257, seed=1), (rng.uniform(-3, 3, (33, 3)), rng.uniform(1, 2, 33)),
+               fs.workloads.globule(1000, seed=2, offset=(-400.0, 250.0, 90.0))]
+    for alg, res, tol in [(0, 20, LR_TOL_FP32), (1, 100, SR_TOL)]:
+        outs = eng32.calc_batch(alg, structs, 1.4, res)
+        for (x, r), got in zip(structs, outs):
+            assert got.shape == r.shape
+            assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
+
+
+def test_large_probe_and_radii(eng32):
+    """Probe and radii far outside the protein range: many more neighbours per atom, coarse grid."""
+    x, r = fs.workloads.globule(900, seed=5)
+    for probe in (0.0, 3.0, 6.0):
+        for alg, res, tol in [(0, 16, LR_TOL_FP32), (1, 100, SR_TOL)]:
+            assert maxerr(eng32.calc(alg, x, r, probe, res), ob.oracle_calc(x, r, alg, probe, res)) < tol, (probe, alg)
+
+
 def test_zero_probe(eng32):
     x, r = fs.workloads.globule(800, seed=3)
     for alg, res, tol in [(0, 20, LR_TOL_FP32), (1, 100, SR_TOL)]:
