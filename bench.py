@@ -143,7 +143,7 @@ def run_reference_arm(args, rank):
         times.append(dt)
     total = float(np.sum(times))
     value = N_ATOMS * args.steps / total
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -152,10 +152,33 @@ def run_reference_arm(args, rank):
                          "sample": "full 100k-atom structure per step, freesasa_calc_coord wall clock"},
         "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner to fd 1)
+    must not pollute it: point fd 1 at stderr for the rest of the run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -198,6 +221,7 @@ def main():
     d_all = torch.zeros(world * N_ATOMS, dtype=torch.float64, device=dev) if distributed else None
     h_all = torch.empty(world * N_ATOMS, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    align = torch.zeros(1, device=dev)
     eng = fs.Engine(local_rank, fs.FP32)
     stream = torch.cuda.Stream(dev)  # a real (non-legacy) stream: the engine replays its launch sequence as a CUDA graph on it
     torch.cuda.set_stream(stream)
@@ -238,6 +262,9 @@ def main():
         barrier()
         for k in range(args.steps):
             flush.fill_(k & 0xFF)  # evict L2 between timed steps (outside the timed events)
+            if distributed:
+                dist.all_reduce(align)  # ranks leave the (untimed) flush together: the step's all-gather then
+                # only waits for differences in compute time, not for flush/launch skew between ranks
             ev0[k].record(stream)
             device_step()
             ev1[k].record(stream)
@@ -312,7 +339,7 @@ def main():
             if nn_pairs:
                 line["roofline"]["compute"] = {"pair_slice_evals_per_s": nn_pairs * N_SLICES / (k_ms * 1e-3),
                                                "pair_slice_evals": nn_pairs * N_SLICES}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
