@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace fsb200;
@@ -197,6 +198,54 @@ int ensure_points(fsb200_ctx *c, int n_points, cudaStream_t stream)
 // overhead per call on the 100k-atom benchmark, 4x on the 1024-structure batch).
 constexpr size_t kStageChunk = 1u << 20;
 constexpr size_t kStageMax = 1ull << 30;   // beyond this fall back to plain pageable copies
+
+constexpr size_t kParallelCopyBytes = 16u << 20;
+constexpr int kCopyThreads = 4;
+
+// fn(k) for every structure k, the structures split into kCopyThreads contiguous groups of similar total
+// size (offsets = prefix sums of atom counts).  A single huge structure is one unit: callers with one
+// structure get their parallelism from splitting it themselves (see below).
+void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+    if (bytes < (4u << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t part = (bytes / kCopyThreads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < kCopyThreads; ++t) {
+        const size_t o = part * t;
+        if (o >= bytes) break;
+        const size_t m = bytes - o < part ? bytes - o : part;
+        unsigned char *d = static_cast<unsigned char *>(dst) + o;
+        const unsigned char *s = static_cast<const unsigned char *>(src) + o;
+        if (t + 1 < kCopyThreads && o + m < bytes) pool.emplace_back([=]() { std::memcpy(d, s, m); });
+        else std::memcpy(d, s, bytes - o);
+        if (!(t + 1 < kCopyThreads && o + m < bytes)) break;
+    }
+    for (auto &th : pool) th.join();
+}
+
+template <typename F> void parallel_over_bytes(int n_struct, const int *offsets, F fn)
+{
+    if (n_struct < 2 * kCopyThreads) {
+        for (int k = 0; k < n_struct; ++k) fn(k);  // few (possibly huge) structures: fn splits each copy itself
+        return;
+    }
+    std::vector<std::thread> pool;
+    const long long total = offsets[n_struct];
+    int begin = 0;
+    for (int t = 0; t < kCopyThreads; ++t) {
+        const long long target = total * (t + 1) / kCopyThreads;
+        int end = begin;
+        while (end < n_struct && (offsets[end + 1] <= target || t == kCopyThreads - 1)) ++end;
+        if (t == kCopyThreads - 1) end = n_struct;
+        if (t + 1 < kCopyThreads) pool.emplace_back([=]() { for (int k = begin; k < end; ++k) fn(k); });
+        else for (int k = begin; k < end; ++k) fn(k);
+        begin = end;
+    }
+    for (auto &th : pool) th.join();
+}
 
 int ensure_stage(fsb200_ctx *c, size_t bytes)
 {
@@ -517,7 +566,17 @@ int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_ato
     cudaStream_t st = c->stream;
     const size_t in_bytes = 32 * (size_t)n, out_bytes = 8 * (size_t)n;
     const bool staged = in_bytes + out_bytes <= kStageMax;
-    if (staged) {
+    const bool threaded = staged && in_bytes >= kParallelCopyBytes;  // big transfers: several host threads fill the staging buffer
+    if (threaded) {
+        if (ensure_stage(c, in_bytes + out_bytes)) return FSB200_FAIL;
+        unsigned char *hx = c->h_stage, *hr = c->h_stage + 24 * (size_t)n;
+        parallel_over_bytes(n_struct, off.data(), [&](int k) {
+            parallel_memcpy(hx + 24 * (size_t)off[k], xyz[k], sizeof(double) * 3 * (size_t)n_atoms[k]);
+            parallel_memcpy(hr + 8 * (size_t)off[k], radii[k], sizeof(double) * (size_t)n_atoms[k]);
+        });
+        CU(cudaMemcpyAsync(c->in_xyz.p, hx, 24 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->in_radii.p, hr, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    } else if (staged) {
         if (ensure_stage(c, in_bytes + out_bytes)) return FSB200_FAIL;
         for (int k = 0; k < n_struct; ++k) {
             if (staged_h2d(c, c->in_xyz.p + 3 * (size_t)off[k], xyz[k], sizeof(double) * 3 * (size_t)n_atoms[k], 24 * (size_t)off[k], st)) return FSB200_FAIL;
@@ -541,7 +600,9 @@ int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_ato
         return FSB200_SUCCESS;
     };
     const int rc = run_pipeline(c, rq, download);
-    if (rc == FSB200_SUCCESS && staged)
+    if (rc == FSB200_SUCCESS && threaded)
+        parallel_over_bytes(n_struct, off.data(), [&](int k) { parallel_memcpy(sasa[k], h_out + off[k], sizeof(double) * (size_t)n_atoms[k]); });
+    else if (rc == FSB200_SUCCESS && staged)
         for (int k = 0; k < n_struct; ++k) std::memcpy(sasa[k], h_out + off[k], sizeof(double) * (size_t)n_atoms[k]);
     return rc;
 }
