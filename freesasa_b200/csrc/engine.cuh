@@ -61,29 +61,30 @@ enum CounterSlot {
     kCtrCount = 16
 };
 
+// Plain data (no default member initialisers): api.cu zero-fills it and uses the bytes as the graph cache key.
 struct Workspace {
     // inputs (device)
-    const double *xyz = nullptr;    // 3n AoS
-    const double *radii = nullptr;  // n, without probe
-    int n = 0;
-    int n_struct = 1;
-    double probe = 0;
+    const double *xyz;    // 3n AoS
+    const double *radii;  // n, without probe
+    int n;
+    int n_struct;
+    double probe;
     // per-structure
-    int *offsets = nullptr;                 // n_struct+1
-    unsigned long long *bounds = nullptr;   // 7 per structure, order-preserving encoding of doubles
-    GridDesc *grid = nullptr;
+    int *offsets;                 // n_struct+1
+    unsigned long long *bounds;   // 7 per structure, order-preserving encoding of doubles
+    GridDesc *grid;
     // per-atom / per-cell
-    int total_cells_cap = 0;
-    int *cell_of = nullptr;      // n     global cell id of each atom (caller order)
-    int *cell_start = nullptr;   // total_cells_cap + 1  histogram -> exclusive scan
-    int *cell_fill = nullptr;    // total_cells_cap
-    int *slot_atom = nullptr;    // n     atom index by slot (unordered inside a cell)
-    double4 *atoms = nullptr;    // n     sorted {x,y,z,R=r+probe}
-    int *perm = nullptr;         // n     sorted position -> caller index
-    Item *items = nullptr;       // n
-    int *scan_tmp = nullptr;     // block sums for the scan
-    int *counters = nullptr;     // kCtrCount ints
-    int *overflow = nullptr;     // n     sorted positions of overflow atoms
+    int total_cells_cap;
+    int *cell_of;      // n     global cell id of each atom (caller order)
+    int *cell_start;   // total_cells_cap + 1  histogram -> exclusive scan
+    int *cell_fill;    // total_cells_cap
+    int *slot_atom;    // n     atom index by slot (unordered inside a cell)
+    double4 *atoms;    // n     sorted {x,y,z,R=r+probe}
+    int *perm;         // n     sorted position -> caller index
+    Item *items;       // n
+    int *scan_tmp;     // block sums for the scan
+    int *counters;     // kCtrCount ints
+    int *overflow;     // n     sorted positions of overflow atoms
 };
 
 struct IntegrateArgs {

@@ -1,27 +1,31 @@
-// freesasa_b200/csrc/integrate.cu — the two surface integrators as persistent sm_100a kernels.
+// freesasa_b200/csrc/integrate.cu — the two surface integrators as ONE persistent sm_100a kernel template.
 //
-// One CTA = 8 warps; one work item = up to 8 atoms of one grid cell, one warp per atom.
-// Per item the 27-cell neighbourhood (9 contiguous runs of the cell-sorted atom array, because x
-// is the fastest cell coordinate) is staged into shared memory with TMA bulk copies
-// (cp.async.bulk + mbarrier, SASS UBLKCP).  Each warp then
-//   1. filters the staged candidates with the reference's exact fp64 contact test
-//      dx*dx+dy*dy+dz*dz < (Ri+Rj)^2 (src/nb.c:483-491) and ballot-compacts the hits into its
-//      private shared-memory list, expressed in the atom-local frame (differences formed in fp64,
-//      then rounded) — the neighbour SET is therefore identical to the reference's, without its
-//      ~10 % duplicate entries (forward-cell rule, src/nb.c:103-110) and without any global
-//      adjacency array;
-//   2. Lee & Richards (src/sasa_lr.c:270-408): lanes = neighbours.  Per slice every lane derives
-//      its neighbour's buried arc [beta-alpha, beta+alpha]; arcs are ballot-compacted to shared
-//      memory and merged without sorting:  exposed = sum_k max(0, s_k - max(W, P_k)) +
-//      max(0, 2pi - max_k e_k), P_k = max{e_m : (s_m,m) < (s_k,k)}, W = wrapped coverage.
-//      beta = atan2(dy,dx)+pi is slice-invariant and hoisted out of the slice loop (the reference
-//      recomputes it per slice, src/sasa_lr.c:337).  alpha uses the cancellation-free half-angle
-//      form tan^2(alpha/2) = (a+b-d)(d+b-a) / ((d+a-b)(a+b+d)) instead of acos of a quotient.
-//   3. Shrake & Rupley (src/sasa_sr.c:276-338): lanes = test points.  Point u of atom i is hidden
-//      by neighbour a iff u.D_a >= t_a with D_a = x_a - x_i, t_a = (Ri^2+|D_a|^2-Ra^2)/(2Ri)
-//      (algebraically the reference's |Ri u + x_i - x_a|^2 <= Ra^2): 3 FMA + compare per test in
-//      fp32; results inside a rounding band are re-decided by replaying the reference's exact
-//      fp64 expression, so every inside/outside decision equals the reference's.
+// Scheduling (details at k_integrate): every CTA keeps a ring of two shared-memory tiles.  A tile holds the
+// 27-cell neighbourhood of one work item (<= 16 atoms of one grid cell): 9 contiguous runs of the
+// cell-sorted atom array (x is the fastest cell coordinate), staged with TMA bulk copies
+// (cp.async.bulk + mbarrier, SASS UBLKCP).  The CTA's 14 warps are independent: each claims ONE atom at a
+// time with a compare-and-swap, and the warp that completes the last neighbour gather of a tile recycles it
+// from the global work queue while everybody else is already integrating.
+//
+// Per atom, one warp:
+//   1. gather      filters the staged candidates with the reference's exact fp64 contact test
+//                  dx*dx+dy*dy+dz*dz < (Ri+Rj)^2 (src/nb.c:483-491) and ballot-compacts the hits into its
+//                  private shared-memory list in the atom-local frame (differences formed in fp64, then
+//                  rounded).  The neighbour SET equals the reference's, without its ~10 % duplicate entries
+//                  (forward-cell rule, src/nb.c:103-110) and without any global adjacency array.
+//   2. Lee & Richards (src/sasa_lr.c:270-408), lanes = neighbours:
+//        lr_atom_fastk<3>   fp32, <= 96 neighbours (the production path): z-sorted records in registers,
+//                           burial vote, sector-mask full-cover early-out, tiny exact merge of what is left
+//        lr_atom_fast       fp32, 97..kNbCap neighbours: all arcs of a slice merged pairwise with unique keys
+//        lr_atom<T>         generic (fp64 validation mode; fp32 in the global-memory overflow kernel)
+//      All three use the cancellation-free half-angle form tan^2(alpha/2) = (a+b-d)(d+b-a)/((d+a-b)(a+b+d))
+//      instead of acos of a quotient (src/sasa_lr.c:335) and hoist beta = atan2(dy,dx)+pi out of the slice
+//      loop (the reference recomputes it per slice, :337).
+//   3. Shrake & Rupley (src/sasa_sr.c:276-338), lanes = test points (sr_atom): point u of atom i is hidden by
+//      neighbour a iff u.D_a >= t_a, D_a = x_a - x_i, t_a = (Ri^2+|D_a|^2-Ra^2)/(2Ri) — algebraically the
+//      reference's |Ri u + x_i - x_a|^2 <= Ra^2.  3 FMA + compare per test in fp32; tests inside a rounding
+//      band are re-decided by replaying the reference's exact fp64 expression, so every inside/outside
+//      decision equals the reference's.
 #include "engine.cuh"
 
 namespace fsb200 {
@@ -410,10 +414,10 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
     return delta * Ri_d * acc;
 }
 
-// ---- step 2c: the common case, at most 96 neighbours (K = 1, 2 or 3 records per lane) -----------------
-// The (z-sorted) records live in REGISTERS, two per lane, for all slices of the atom.  Per slice:
-//   1. both halves evaluate their circle-circle configuration; a half whose neighbours are all out of
-//      z-range is skipped (the records are z-sorted, so low slices skip the upper half and vice versa);
+// ---- step 2c: the common case, at most 32 K neighbours, K records per lane (instantiated with K = 3) ----
+// The (z-sorted) records live in REGISTERS, K per lane, for all slices of the atom.  Per slice:
+//   1. each group of 32 records evaluates its circle-circle configurations; a group whose neighbours are
+//      all out of z-range is skipped (the records are z-sorted, so low slices skip the upper groups);
 //   2. one vote: some circle swallows the slice circle -> the slice is buried (src/sasa_lr.c:327);
 //   3. angles are measured in SECTORS (1/32 of the circle, so pi is exactly 16): every arc marks the
 //      sectors it covers completely in a 32-bit mask, one REDUX.OR gives the sectors covered by a single
