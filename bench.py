@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-certificate", action="store_true",
+                    help="ablation: integrate every atom, do not use the buried-atom certificate (results are identical)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -223,6 +225,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     align = torch.zeros(1, device=dev)
     eng = fs.Engine(local_rank, fs.FP32)
+    if args.no_certificate:
+        eng.set_certificate(False)
     stream = torch.cuda.Stream(dev)  # a real (non-legacy) stream: the engine replays its launch sequence as a CUDA graph on it
     torch.cuda.set_stream(stream)
 
@@ -269,6 +273,7 @@ def main():
             device_step()
             ev1[k].record(stream)
             st = eng.stats()
+            certified = st["n_certified"]
             integrate_ms.append(st["integrate_ms"])
             device_ms.append(st["device_ms"])
         barrier()
@@ -302,6 +307,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "atoms_per_gpu": N_ATOMS, "structures": world,
+                       "buried_atom_certificate": ("off (ablation)" if args.no_certificate else
+                                                   f"on: {certified} of {N_ATOMS} atoms proved fully buried, not integrated (exact, DESIGN.md)"),
                        "l2": "flushed between timed steps (256 MiB device write, outside the events)",
                        "timing": "CUDA events on the launching stream, sum over steps, max over ranks",
                        "collective": "one NCCL all-gather of per-atom SASA per step" if distributed else "none (N=1)"},

@@ -71,7 +71,8 @@ class Stats(ctypes.Structure):
 
     _fields_ = [
         ("n_atoms", ctypes.c_int), ("n_structures", ctypes.c_int), ("n_items", ctypes.c_int),
-        ("n_overflow", ctypes.c_int), ("max_neighbours", ctypes.c_int), ("kernel_launches", ctypes.c_int),
+        ("n_overflow", ctypes.c_int), ("max_neighbours", ctypes.c_int), ("n_certified", ctypes.c_int),
+        ("kernel_launches", ctypes.c_int),
         ("device_ms", ctypes.c_float), ("integrate_ms", ctypes.c_float),
     ]
 
@@ -124,6 +125,7 @@ def _engine_lib():
         L.fsb200_ctx_destroy.restype = None
         L.fsb200_ctx_destroy.argtypes = [vp]
         L.fsb200_ctx_set_precision.argtypes = [vp, ctypes.c_int]
+        L.fsb200_ctx_set_certificate.argtypes = [vp, ctypes.c_int]
         L.fsb200_ctx_stats.argtypes = [vp, ctypes.POINTER(Stats)]
         L.fsb200_ctx_calc.argtypes = [vp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_int]
         L.fsb200_ctx_calc_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, _ip, _dpp, _dpp, _dpp, ctypes.c_double, ctypes.c_int]
@@ -270,6 +272,10 @@ class Engine:
         self._check(self._L.fsb200_ctx_set_precision(self._ctx, int(precision)), "fsb200_ctx_set_precision")
         self.precision = int(precision)
 
+    def set_certificate(self, on: bool):
+        """Buried-atom certificate on/off (default on; never changes a result, only the time)."""
+        self._check(self._L.fsb200_ctx_set_certificate(self._ctx, 1 if on else 0), "fsb200_ctx_set_certificate")
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self._L.fsb200_ctx_stats(self._ctx, ctypes.byref(s)), "fsb200_ctx_stats")
@@ -300,7 +306,8 @@ class Engine:
         out = np.empty(n, dtype=np.int32)
         self._check(self._L.fsb200_ctx_neighbour_counts(self._ctx, out.ctypes.data_as(_ip), _ptr(xyz), _ptr(radii), n,
                                                         float(probe)), "fsb200_ctx_neighbour_counts")
-        return out
+        self.last_certified = (out >> 30) & 1  # atoms settled by the buried-atom certificate in that pass
+        return out & 0x3FFFFFFF
 
     # ---- device-resident path: torch CUDA tensors (float64) in, torch tensor out -------------------------
     def calc_device(self, alg: int, d_xyz, d_radii, probe: float = 1.4, resolution: int = 20, offsets=None,

@@ -93,6 +93,9 @@ struct fsb200_ctx {
     DevBuf<Item> items;
     DevBuf<unsigned char> scratch;
     // Shrake-Rupley test points of the last resolution used
+    // probe directions of the buried-atom certificate (uploaded once per context)
+    DevBuf<float4> cert_points;
+    bool use_certificate = true;
     int sr_points = 0;
     DevBuf<float4> points_f;
     DevBuf<double> points_d;
@@ -319,6 +322,7 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
         ia.points_f = c->points_f.p;
         ia.points_d = c->points_d.p;
     }
+    ia.cert_points = c->use_certificate ? c->cert_points.p : nullptr;
     int &ctas = c->grid_ctas[rq.alg][c->precision];
     if (ctas == 0) ctas = integrate_grid_ctas(rq.alg, c->precision, c->device);
     ia.grid_ctas = ctas;
@@ -366,6 +370,7 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     s.n_structures = rq.n_struct;
     s.n_items = c->h_status[kCtrItems];
     s.n_overflow = c->h_status[kCtrOverflow];
+    s.n_certified = c->h_status[kCtrCertified];
     s.max_neighbours = 0;
     if (c->h_status[kCtrBadInput]) {
         g_launches += launches;
@@ -504,6 +509,13 @@ fsb200_ctx *fsb200_ctx_create(int device)
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_status, sizeof(int) * kCtrCount) == cudaSuccess;
+    if (ok) {  // the certificate's probe set: the same patch-ordered golden spiral the S&R path uses, 128 points
+        std::vector<double> pd;
+        std::vector<float4> pf;
+        make_test_points(kCertPoints, pd, pf);
+        ok = c->cert_points.ensure(pf.size()) == cudaSuccess &&
+             cudaMemcpy(c->cert_points.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) {
         fail("could not initialise context on device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
         fsb200_ctx_destroy(c);
@@ -521,7 +533,7 @@ void fsb200_ctx_destroy(fsb200_ctx *c)
     c->offsets.release(); c->cell_of.release(); c->cell_start.release(); c->cell_fill.release();
     c->slot_atom.release(); c->perm.release(); c->scan_tmp.release(); c->counters.release();
     c->overflow.release(); c->bounds.release(); c->grid.release(); c->atoms.release();
-    c->items.release(); c->scratch.release(); c->points_f.release(); c->points_d.release();
+    c->items.release(); c->scratch.release(); c->points_f.release(); c->points_d.release(); c->cert_points.release();
     for (int k = 0; k < 4; ++k)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -536,6 +548,13 @@ int fsb200_ctx_set_precision(fsb200_ctx *c, int precision)
     if (!c) return fail("null context");
     if (precision != FSB200_FP32 && precision != FSB200_FP64) return fail("unknown precision %d", precision);
     c->precision = precision;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ctx_set_certificate(fsb200_ctx *c, int on)
+{
+    if (!c) return fail("null context");
+    c->use_certificate = on != 0;
     return FSB200_SUCCESS;
 }
 

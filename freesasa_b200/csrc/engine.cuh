@@ -28,6 +28,7 @@ constexpr int kRingSlots = 2;               // tiles in flight per CTA
 constexpr int kItemAtoms = 16;              // one work item = up to 16 consecutive atoms of one cell
 constexpr int kTileCap = 640;               // atoms of the 27-cell neighbourhood staged in smem (20 KB)
 constexpr int kNbCap = 160;                 // per-warp neighbour list capacity in smem
+constexpr int kCertPoints = 128;           // probe directions of the buried-atom certificate
 constexpr int kCellsPerAtomCap = 2;         // grid budget: cells <= 2*n_k + 64 per structure
 constexpr int kCellsSlack = 64;
 
@@ -58,6 +59,8 @@ enum CounterSlot {
     kCtrBadInput = 4,   // non-finite coordinate or radius seen
     kCtrQueue2 = 5,     // queue head of the overflow kernel
     kCtrStalled = 6,    // a warp gave up waiting for a tile (internal error, reported to the host)
+    // 7..15: post-mortem of a stall; kCtrCertified shares slot 15 (only meaningful when nothing stalled)
+    kCtrCertified = 15, // atoms proved completely buried by the coverage certificate (area 0 without integration)
     kCtrCount = 16
 };
 
@@ -99,6 +102,7 @@ struct IntegrateArgs {
     const float4 *points_f;   // SR: unit test points, float
     const double *points_d;   // SR: unit test points, 3*resolution doubles (bit-identical to the reference's)
     int grid_ctas;
+    const float4 *cert_points;  // kCertPoints unit vectors for the buried-atom certificate, or nullptr (off)
 };
 
 // cells.cu

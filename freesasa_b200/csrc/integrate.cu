@@ -113,11 +113,12 @@ __host__ __device__ constexpr int arc_cap(int cap) { return cap + 4 > 132 ? cap 
 
 template <int ALG, typename T> struct WarpLayout {
     // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
-    //   L&R: records + arc_cap(cap) arcs of the current slice + their exact starts;  S&R: records + candidate indices
+    //   L&R: records + arc_cap(cap) arcs of the current slice + their exact starts (the certificate's thresholds
+    //        live in the starts array before the slices begin);  S&R: records + candidate indices + thresholds
     static __host__ __device__ constexpr size_t bytes(int cap)
     {
         return ALG == 0 ? (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * (sizeof(Arc<T>) + sizeof(T))
-                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int));
+                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int) + sizeof(float));
     }
 };
 
@@ -698,23 +699,87 @@ __device__ __forceinline__ double sr_atom(Rec4<T> *recs, int *cidx, const double
     return (4.0 * 3.14159265358979323846 * s.R * s.R * exposed) / npts;
 }
 
+// ---- buried-atom certificate ---------------------------------------------------------------------------
+// Most atoms of a large structure have NO exposed surface (92 % of the 100k-atom benchmark globule), and
+// for them every slice ends "buried" or "fully covered" and every test point is hidden.  This routine proves
+// that outcome for a whole atom at once, at ~5 % of the cost of integrating it:
+//   * kCertPoints probe directions u_k (golden spiral) cover the unit sphere with patches of angular radius
+//     rho = 14.5 deg (measured covering radius 13.82 deg + probe-set resolution 0.25 deg, tests/test_certificate.py);
+//   * neighbour a hides the cap of half-angle theta_a around D_a, cos(theta_a) = t_a/|D_a|,
+//     t_a = (Ri^2+|D_a|^2-Ra^2)/(2Ri); it hides the WHOLE patch k iff angle(u_k, D_a) <= theta_a - rho, i.e.
+//     u_k.D_a >= |D_a| cos(theta_a - rho) = t_a cos(rho) + sqrt(|D_a|^2 - t_a^2) sin(rho)  (=: t'_a, plus an
+//     fp32 safety margin);
+//   * if every patch is hidden entirely by a single neighbour, every point of the sphere is strictly inside
+//     some neighbour sphere, so every Lee-Richards slice circle is covered with positive overlap and every
+//     Shrake-Rupley point is hidden: the reference's area is exactly 0 (its arc sweep returns 0 + 2pi - 2pi,
+//     src/sasa_lr.c:389-408; its point count is 0) and so is ours.
+// The test is conservative — a certified atom is always truly buried (never the other way round) — so it
+// changes no result, only the time (tests: certificate on/off give bit-identical arrays).
+constexpr float kCertCos = 0.96814764f;   // cos(14.5 deg)
+constexpr float kCertSin = 0.25038000f;   // sin(14.5 deg)
+
+template <typename T, bool HAS_T>   // HAS_T: recs hold {dx,dy,dz,t} (S&R); otherwise raw {dx,dy,dz,Ra} (L&R)
+__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float *tp, int nn, float Ri, const float4 *cpts, int lane)
+{
+    for (int j = lane; j < nn; j += 32) {
+        const Rec4<T> r = recs[j];
+        const float dx = (float)r.a, dy = (float)r.b, dz = (float)r.c;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        const float d = sqrtf(d2);
+        const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
+        float v = 3.0e38f;                                 // cap narrower than a patch: useless
+        if (t <= -d) v = -3.0e38f;                         // sphere i lies entirely inside sphere a
+        else if (t < d * kCertCos) v = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
+        tp[j] = v;
+    }
+    __syncwarp();
+    const int nn4 = (nn + 3) & ~3;
+    int k_start = 0;
+    for (int g = 0; g < kCertPoints; g += 32) {
+        const float4 u = cpts[g + lane];
+        bool cov = false;
+        int kb = k_start;
+        for (int done = 0; done < nn4; done += 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = kb + i;
+                if (k < nn) {
+                    const Rec4<T> r = recs[k];             // warp-uniform address: broadcast
+                    cov = cov || fmaf(u.x, (float)r.a, fmaf(u.y, (float)r.b, u.z * (float)r.c)) >= tp[k];
+                }
+            }
+            if (__all_sync(kFull, cov)) {
+                k_start = kb;
+                break;
+            }
+            kb += 4;
+            if (kb >= nn4) kb = 0;
+        }
+        if (!__all_sync(kFull, cov)) return false;         // some patch is not provably hidden: integrate normally
+    }
+    return true;
+}
+
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
 template <int ALG, typename T> struct WarpMem {
     Rec4<T> *recs;
     Arc<T> *arcs;      // L&R: arc_cap(cap) arcs of the current slice
     T *starts;         // L&R fp32 fast path: exact arc starts
     int *cidx;         // S&R only
+    float *cert_t;     // thresholds of the buried-atom certificate (cap floats)
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
         arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
         starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * sizeof(Arc<T>));
         cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        cert_t = ALG == 0 ? reinterpret_cast<float *>(starts)
+                          : reinterpret_cast<float *>(mem + (size_t)cap * (sizeof(Rec4<T>) + sizeof(int)));
     }
 };
 
 template <int ALG, typename T, bool FAST>
-__device__ __forceinline__ void finish_atom(const Workspace &ws, const IntegrateArgs &args, const WarpMem<ALG, T> &wm,
+__device__ __forceinline__ bool finish_atom(const Workspace &ws, const IntegrateArgs &args, const WarpMem<ALG, T> &wm,
                                             const double4 *cand_base, const Self &s, int nn, int cap, int pos,
                                             bool allow_overflow, int lane)
 {
@@ -724,11 +789,18 @@ __device__ __forceinline__ void finish_atom(const Workspace &ws, const Integrate
             ws.overflow[atomicAdd(ws.counters + kCtrOverflow, 1)] = pos;
             atomicMax(ws.counters + kCtrMaxCand, nn);
         }
-        return;
+        return false;
     }
     double area = 0.0;
+    bool certified = false;
     if (s.R > 0.0) {
-        if (ALG == 0) {
+        if constexpr (FAST && sizeof(T) == 4) {
+            if (args.cert_points != nullptr && nn > 0)
+                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_t, nn, (float)s.R, args.cert_points, lane);
+        }
+        if (certified) {
+            // area stays 0: proved completely buried
+        } else if (ALG == 0) {
             if constexpr (FAST && sizeof(T) == 4) {
                 Rec4<float> *recs = reinterpret_cast<Rec4<float> *>(wm.recs);
                 KeyArc *arcs = reinterpret_cast<KeyArc *>(wm.arcs);
@@ -751,8 +823,9 @@ __device__ __forceinline__ void finish_atom(const Workspace &ws, const Integrate
     if (lane == 0) {
         const int i = ws.perm[pos];
         args.out[args.sorted_output ? pos : i] = area;
-        if (args.nn_out) args.nn_out[i] = nn;
+        if (args.nn_out) args.nn_out[i] = nn | (certified ? (1 << 30) : 0);
     }
+    return certified;
 }
 
 __device__ __forceinline__ Self load_self(const double4 me)
@@ -902,6 +975,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], s, lane);
 
     long long wait_since = 0;
+    int n_certified = 0;
     for (;;) {
         // ---- claim one atom (lane 0 negotiates, the warp follows) ----------------------------------------
         // The slot's claim word names the fill it hosts.  Only when that is the fill `cur` points at do we
@@ -992,9 +1066,10 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         if (g == n_atoms) fill_slot(ws, args, n_items, sl, tile, &full[s], f + kRingSlots, lane);  // last gather: recycle the slot
 
         // ---- integrate (no shared state besides the warp's own lists) -----------------------------------------
-        if (mine) finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane);
+        if (mine) n_certified += finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane) ? 1 : 0;
         __syncwarp();
     }
+    if (lane == 0 && n_certified) atomicAdd(ws.counters + kCtrCertified, n_certified);
 }
 
 // Atoms whose neighbour list exceeded kNbCap: one warp per atom, lists in global scratch.

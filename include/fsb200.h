@@ -52,6 +52,7 @@ typedef struct fsb200_stats {
     int n_items;             /* work items (cell chunks) integrated */
     int n_overflow;          /* atoms that took the large-neighbourhood path */
     int max_neighbours;      /* largest neighbour count seen by the overflow path (0 if unused) */
+    int n_certified;         /* atoms proved completely buried (area exactly 0) without being integrated */
     int kernel_launches;     /* kernels launched by this call */
     float device_ms;         /* device time of the call, CUDA events on the call's stream */
     float integrate_ms;      /* device time of the integration kernel alone */
@@ -79,6 +80,9 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
 fsb200_ctx *fsb200_ctx_create(int device); /* NULL on failure */
 void fsb200_ctx_destroy(fsb200_ctx *ctx);
 int fsb200_ctx_set_precision(fsb200_ctx *ctx, int precision);
+/* The buried-atom certificate (fp32 mode) proves "no exposed surface" for most interior atoms and skips their
+ * integration; it never changes a result.  On by default; off is for ablation and tests. */
+int fsb200_ctx_set_certificate(fsb200_ctx *ctx, int on);
 int fsb200_ctx_calc(fsb200_ctx *ctx, int alg, double *sasa, const double *xyz, const double *radii,
                     int n, double probe, int resolution);
 int fsb200_ctx_calc_batch(fsb200_ctx *ctx, int alg, int n_struct, const int *n_atoms,
@@ -113,7 +117,8 @@ int fsb200_ctx_unpermute(fsb200_ctx *ctx, const double *d_sorted, double *d_out,
 
 /* ---- test hook ------------------------------------------------------------------------------ */
 /* Per-atom neighbour counts |{j != i : |x_i-x_j|^2 < (R_i+R_j)^2}| as the engine's cell list sees
- * them (parity check for the src/nb.c row of the scope table). */
+ * them (parity check for the src/nb.c row of the scope table).  Bit 30 of a count is set when the atom was
+ * settled by the buried-atom certificate. */
 int fsb200_ctx_neighbour_counts(fsb200_ctx *ctx, int *counts, const double *xyz, const double *radii,
                                 int n, double probe);
 
