@@ -728,7 +728,9 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float *tp, i
         const float d = sqrtf(d2);
         const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
         float v = 3.0e38f;                                 // cap narrower than a patch: useless
-        if (t <= -d) v = -3.0e38f;                         // sphere i lies entirely inside sphere a
+        if (t < -d - 1e-4f * (d + Ri)) v = -3.0e38f;       // sphere i lies strictly inside sphere a (coincident
+                                                           // equal spheres, t = d = 0, are NOT: the reference
+                                                           // decides their points one rounding at a time)
         else if (t < d * kCertCos) v = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
         tp[j] = v;
     }
