@@ -514,7 +514,8 @@ fsb200_ctx *fsb200_ctx_create(int device)
         std::vector<float4> pf;
         make_test_points(kCertPoints, pd, pf);
         ok = c->cert_points.ensure(pf.size()) == cudaSuccess &&
-             cudaMemcpy(c->cert_points.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice) == cudaSuccess;
+             cudaMemcpy(c->cert_points.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice) == cudaSuccess &&
+             set_cert_points(pf.data()) == 0;
     }
     if (!ok) {
         fail("could not initialise context on device %d: %s", device, cudaGetErrorString(cudaGetLastError()));

@@ -102,7 +102,7 @@ struct IntegrateArgs {
     const float4 *points_f;   // SR: unit test points, float
     const double *points_d;   // SR: unit test points, 3*resolution doubles (bit-identical to the reference's)
     int grid_ctas;
-    const float4 *cert_points;  // kCertPoints unit vectors for the buried-atom certificate, or nullptr (off)
+    const float4 *cert_points;  // non-null: use the buried-atom certificate (the directions themselves live in constant memory)
 };
 
 // cells.cu
@@ -114,6 +114,7 @@ int launch_overflow(const Workspace &ws, const IntegrateArgs &args, int n_overfl
 size_t overflow_scratch_bytes(int n_warps, int list_cap, int precision);
 int overflow_warps(int n_overflow);
 int integrate_grid_ctas(int alg, int precision, int device);
+int set_cert_points(const float4 *host_points);   // kCertPoints probe directions -> constant memory of the current device
 int launch_unpermute(const int *perm, const double *sorted, double *out, int n, cudaStream_t stream);
 
 // ---- small device helpers --------------------------------------------------------------------

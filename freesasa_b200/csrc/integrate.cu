@@ -110,15 +110,16 @@ template <> struct Consts<double> {
 // arcs one slice can produce: every neighbour (+4 sentinels) in the general paths, at most
 // 96 + 32 synthetic + 4 sentinels in the <= 96-neighbour path
 __host__ __device__ constexpr int arc_cap(int cap) { return cap + 4 > 132 ? cap + 4 : 132; }
+constexpr int kCertList = 64;   // neighbours the buried-atom certificate works with (16 B each; fits the L&R arc array)
 
 template <int ALG, typename T> struct WarpLayout {
     // bytes of shared (or scratch) memory one warp needs for a neighbour list of `cap` entries:
-    //   L&R: records + arc_cap(cap) arcs of the current slice + their exact starts (the certificate's thresholds
-    //        live in the starts array before the slices begin);  S&R: records + candidate indices + thresholds
+    //   L&R: records + arc_cap(cap) arcs of the current slice + their exact starts (the certificate's short list
+    //        lives in the arcs array before the slices begin);  S&R: records + candidate indices + that list
     static __host__ __device__ constexpr size_t bytes(int cap)
     {
         return ALG == 0 ? (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * (sizeof(Arc<T>) + sizeof(T))
-                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int) + sizeof(float));
+                        : (size_t)cap * (sizeof(Rec4<T>) + sizeof(int)) + kCertList * sizeof(float4);
     }
 };
 
@@ -717,47 +718,63 @@ __device__ __forceinline__ double sr_atom(Rec4<T> *recs, int *cidx, const double
 // changes no result, only the time (tests: certificate on/off give bit-identical arrays).
 constexpr float kCertCos = 0.96814764f;   // cos(14.5 deg)
 constexpr float kCertSin = 0.25038000f;   // sin(14.5 deg)
+__constant__ float4 c_cert_points[kCertPoints];   // the probe directions (uploaded per device by set_cert_points)
 
+// lanes = neighbours.  Neighbours whose cap is wider than a patch are compacted into a short list (at most
+// kCertList = 64, two per lane, kept in registers); then every probe direction — one uniform constant-memory
+// load — is tested against all of them at once and a single vote says whether some neighbour hides its whole
+// patch.  The first patch nobody hides ends the attempt.
 template <typename T, bool HAS_T>   // HAS_T: recs hold {dx,dy,dz,t} (S&R); otherwise raw {dx,dy,dz,Ra} (L&R)
-__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float *tp, int nn, float Ri, const float4 *cpts, int lane)
+__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list, int nn, float Ri, int lane)
 {
-    for (int j = lane; j < nn; j += 32) {
-        const Rec4<T> r = recs[j];
-        const float dx = (float)r.a, dy = (float)r.b, dz = (float)r.c;
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        const float d = sqrtf(d2);
-        const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
-        float v = 3.0e38f;                                 // cap narrower than a patch: useless
-        if (t < -d - 1e-4f * (d + Ri)) v = -3.0e38f;       // sphere i lies strictly inside sphere a (coincident
-                                                           // equal spheres, t = d = 0, are NOT: the reference
-                                                           // decides their points one rounding at a time)
-        else if (t < d * kCertCos) v = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
-        tp[j] = v;
-    }
-    __syncwarp();
-    const int nn4 = (nn + 3) & ~3;
-    int k_start = 0;
-    for (int g = 0; g < kCertPoints; g += 32) {
-        const float4 u = cpts[g + lane];
-        bool cov = false;
-        int kb = k_start;
-        for (int done = 0; done < nn4; done += 4) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = kb + i;
-                if (k < nn) {
-                    const Rec4<T> r = recs[k];             // warp-uniform address: broadcast
-                    cov = cov || fmaf(u.x, (float)r.a, fmaf(u.y, (float)r.b, u.z * (float)r.c)) >= tp[k];
-                }
+    const unsigned lt = lanemask_lt();
+    int n_useful = 0;
+    bool inside = false;
+    for (int base = 0; base < nn; base += 32) {
+        const int j = base + lane;
+        float4 e = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+        bool useful = false;
+        if (j < nn) {
+            const Rec4<T> r = recs[j];
+            e.x = (float)r.a; e.y = (float)r.b; e.z = (float)r.c;
+            const float d2 = e.x * e.x + e.y * e.y + e.z * e.z;
+            const float d = sqrtf(d2);
+            const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
+            if (t < -d - 1e-4f * (d + Ri)) inside = true;  // sphere i lies strictly inside sphere a (coincident equal
+                                                           // spheres, t = d = 0, do NOT count: the reference decides
+                                                           // their points one rounding at a time)
+            else if (t < d * kCertCos) {                   // cap wider than a patch
+                e.w = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
+                useful = true;
             }
-            if (__all_sync(kFull, cov)) {
-                k_start = kb;
-                break;
-            }
-            kb += 4;
-            if (kb >= nn4) kb = 0;
         }
-        if (!__all_sync(kFull, cov)) return false;         // some patch is not provably hidden: integrate normally
+        const unsigned m = __ballot_sync(kFull, useful);
+        if (useful) {
+            const int slot = n_useful + __popc(m & lt);
+            if (slot < kCertList) list[slot] = e;
+        }
+        n_useful += __popc(m);
+    }
+    if (__any_sync(kFull, inside)) return true;
+    if (n_useful == 0 || n_useful > kCertList) return false;   // nothing to work with / too many for the short list
+    __syncwarp();
+    const float4 none = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+    const float4 n0 = lane < n_useful ? list[lane] : none;
+    const float4 n1 = lane + 32 < n_useful ? list[lane + 32] : none;
+    __syncwarp();                                              // the list's memory is reused by the integrators
+    if (n_useful <= 32) {
+        for (int k = 0; k < kCertPoints; ++k) {
+            const float4 u = c_cert_points[k];                 // uniform address: constant-cache broadcast
+            const bool c = fmaf(u.x, n0.x, fmaf(u.y, n0.y, u.z * n0.z)) >= n0.w;
+            if (!__any_sync(kFull, c)) return false;
+        }
+    } else {
+        for (int k = 0; k < kCertPoints; ++k) {
+            const float4 u = c_cert_points[k];
+            const bool c = fmaf(u.x, n0.x, fmaf(u.y, n0.y, u.z * n0.z)) >= n0.w ||
+                           fmaf(u.x, n1.x, fmaf(u.y, n1.y, u.z * n1.z)) >= n1.w;
+            if (!__any_sync(kFull, c)) return false;
+        }
     }
     return true;
 }
@@ -768,15 +785,15 @@ template <int ALG, typename T> struct WarpMem {
     Arc<T> *arcs;      // L&R: arc_cap(cap) arcs of the current slice
     T *starts;         // L&R fp32 fast path: exact arc starts
     int *cidx;         // S&R only
-    float *cert_t;     // thresholds of the buried-atom certificate (cap floats)
+    float4 *cert_list; // short list of the buried-atom certificate (kCertList entries)
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
         arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
         starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * sizeof(Arc<T>));
         cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
-        cert_t = ALG == 0 ? reinterpret_cast<float *>(starts)
-                          : reinterpret_cast<float *>(mem + (size_t)cap * (sizeof(Rec4<T>) + sizeof(int)));
+        cert_list = ALG == 0 ? reinterpret_cast<float4 *>(arcs)
+                             : reinterpret_cast<float4 *>(mem + (size_t)cap * (sizeof(Rec4<T>) + sizeof(int)));
     }
 };
 
@@ -798,7 +815,7 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
     if (s.R > 0.0) {
         if constexpr (FAST && sizeof(T) == 4) {
             if (args.cert_points != nullptr && nn > 0)
-                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_t, nn, (float)s.R, args.cert_points, lane);
+                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_list, nn, (float)s.R, lane);
         }
         if (certified) {
             // area stays 0: proved completely buried
@@ -1124,6 +1141,11 @@ template <int ALG, typename T> int configure_and_occupancy(int device)
 }
 
 }  // namespace
+
+int set_cert_points(const float4 *host_points)
+{
+    return cudaMemcpyToSymbol(c_cert_points, host_points, sizeof(float4) * kCertPoints) == cudaSuccess ? 0 : -1;
+}
 
 int integrate_grid_ctas(int alg, int precision, int device)
 {
