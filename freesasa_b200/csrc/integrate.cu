@@ -718,7 +718,6 @@ __device__ __forceinline__ double sr_atom(Rec4<T> *recs, int *cidx, const double
 // changes no result, only the time (tests: certificate on/off give bit-identical arrays).
 constexpr float kCertCos = 0.96814764f;   // cos(14.5 deg)
 constexpr float kCertSin = 0.25038000f;   // sin(14.5 deg)
-constexpr float kCertUseful = 0.82412619f; // cos(34.5 deg): only caps of half-angle > rho + 20 deg enter the short list
 __constant__ float4 c_cert_points[kCertPoints];   // the probe directions (uploaded per device by set_cert_points)
 
 // lanes = neighbours.  Neighbours whose cap is wider than a patch are compacted into a short list (at most
@@ -744,9 +743,7 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
             if (t < -d - 1e-4f * (d + Ri)) inside = true;  // sphere i lies strictly inside sphere a (coincident equal
                                                            // spheres, t = d = 0, do NOT count: the reference decides
                                                            // their points one rounding at a time)
-            else if (t < d * kCertUseful) {                // cap at least 20 deg wider than a patch: smaller ones almost
-                                                           // never hide a whole patch alone, and leaving them out keeps
-                                                           // the short list within one record per lane for ~95 % of atoms
+            else if (t < d * kCertCos) {                   // cap wider than a patch
                 e.w = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
                 useful = true;
             }
