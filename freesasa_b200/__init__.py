@@ -74,6 +74,7 @@ class Stats(ctypes.Structure):
         ("n_overflow", ctypes.c_int), ("max_neighbours", ctypes.c_int), ("n_certified", ctypes.c_int),
         ("kernel_launches", ctypes.c_int),
         ("device_ms", ctypes.c_float), ("integrate_ms", ctypes.c_float),
+        ("host_stage_ms", ctypes.c_float), ("host_total_ms", ctypes.c_float),
     ]
 
     def as_dict(self):

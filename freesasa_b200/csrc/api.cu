@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -202,52 +205,95 @@ int ensure_points(fsb200_ctx *c, int n_points, cudaStream_t stream)
 constexpr size_t kStageChunk = 1u << 20;
 constexpr size_t kStageMax = 1ull << 30;   // beyond this fall back to plain pageable copies
 
-constexpr size_t kParallelCopyBytes = 16u << 20;
-constexpr int kCopyThreads = 4;
+// ---- host copy pool ------------------------------------------------------------------------------------
+// Filling the pinned staging buffer is a plain memcpy from the caller's pageable arrays; at 3-200 MB per call
+// one core's ~15 GB/s is the largest host-side cost of an end-to-end call.  Three persistent helper threads
+// (created on first use, parked on a condition variable, never joined: the pool is deliberately leaked so that
+// process exit does not wait on them) plus the calling thread copy 256 KB pieces in parallel.
+constexpr size_t kParallelCopyBytes = 1u << 20;   // below this a single memcpy is faster than waking the pool
+constexpr size_t kCopyPiece = 256u << 10;
 
-// fn(k) for every structure k, the structures split into kCopyThreads contiguous groups of similar total
-// size (offsets = prefix sums of atom counts).  A single huge structure is one unit: callers with one
-// structure get their parallelism from splitting it themselves (see below).
-void parallel_memcpy(void *dst, const void *src, size_t bytes)
+class CopyPool {
+public:
+    static CopyPool &get()
+    {
+        static CopyPool *pool = new CopyPool(3);
+        return *pool;
+    }
+    // fn(t) for t in [0, n_tasks), on the pool's threads and the caller's; returns when all are done
+    void run(int n_tasks, const std::function<void(int)> &fn)
+    {
+        std::lock_guard<std::mutex> one_job_at_a_time(job_lock_);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            n_tasks_ = n_tasks;
+            next_.store(0);
+            active_ = (int)workers_.size();
+            ++generation_;
+        }
+        wake_.notify_all();
+        for (int t; (t = next_.fetch_add(1)) < n_tasks;) fn(t);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return active_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    explicit CopyPool(int n)
+    {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+        for (auto &w : workers_) w.detach();
+    }
+    void loop()
+    {
+        int seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                wake_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                fn = fn_;
+                n = n_tasks_;
+            }
+            for (int t; (t = next_.fetch_add(1)) < n;) (*fn)(t);
+            std::lock_guard<std::mutex> g(m_);
+            if (--active_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, job_lock_;
+    std::condition_variable wake_, done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_tasks_ = 0, active_ = 0, generation_ = 0;
+};
+
+struct CopyJob {
+    void *dst;
+    const void *src;
+    size_t bytes;
+};
+
+// all jobs, cut into kCopyPiece pieces, spread over the pool
+void parallel_copy(const std::vector<CopyJob> &jobs)
 {
-    if (bytes < (4u << 20)) {
-        std::memcpy(dst, src, bytes);
+    struct Piece { unsigned char *d; const unsigned char *s; size_t n; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    for (const CopyJob &j : jobs) {
+        total += j.bytes;
+        for (size_t o = 0; o < j.bytes; o += kCopyPiece)
+            pieces.push_back({static_cast<unsigned char *>(j.dst) + o, static_cast<const unsigned char *>(j.src) + o,
+                              j.bytes - o < kCopyPiece ? j.bytes - o : kCopyPiece});
+    }
+    if (total < kParallelCopyBytes) {
+        for (const Piece &p : pieces) std::memcpy(p.d, p.s, p.n);
         return;
     }
-    std::vector<std::thread> pool;
-    const size_t part = (bytes / kCopyThreads + 4095) & ~(size_t)4095;
-    for (int t = 0; t < kCopyThreads; ++t) {
-        const size_t o = part * t;
-        if (o >= bytes) break;
-        const size_t m = bytes - o < part ? bytes - o : part;
-        unsigned char *d = static_cast<unsigned char *>(dst) + o;
-        const unsigned char *s = static_cast<const unsigned char *>(src) + o;
-        if (t + 1 < kCopyThreads && o + m < bytes) pool.emplace_back([=]() { std::memcpy(d, s, m); });
-        else std::memcpy(d, s, bytes - o);
-        if (!(t + 1 < kCopyThreads && o + m < bytes)) break;
-    }
-    for (auto &th : pool) th.join();
-}
-
-template <typename F> void parallel_over_bytes(int n_struct, const int *offsets, F fn)
-{
-    if (n_struct < 2 * kCopyThreads) {
-        for (int k = 0; k < n_struct; ++k) fn(k);  // few (possibly huge) structures: fn splits each copy itself
-        return;
-    }
-    std::vector<std::thread> pool;
-    const long long total = offsets[n_struct];
-    int begin = 0;
-    for (int t = 0; t < kCopyThreads; ++t) {
-        const long long target = total * (t + 1) / kCopyThreads;
-        int end = begin;
-        while (end < n_struct && (offsets[end + 1] <= target || t == kCopyThreads - 1)) ++end;
-        if (t == kCopyThreads - 1) end = n_struct;
-        if (t + 1 < kCopyThreads) pool.emplace_back([=]() { for (int k = begin; k < end; ++k) fn(k); });
-        else for (int k = begin; k < end; ++k) fn(k);
-        begin = end;
-    }
-    for (auto &th : pool) th.join();
+    CopyPool::get().run((int)pieces.size(), [&](int t) { std::memcpy(pieces[t].d, pieces[t].s, pieces[t].n); });
 }
 
 int ensure_stage(fsb200_ctx *c, size_t bytes)
@@ -580,20 +626,24 @@ int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_ato
         off[k + 1] = off[k] + n_atoms[k];
     }
     const int n = off[n_struct];
+    const auto t_begin = std::chrono::steady_clock::now();
     CU(c->in_xyz.ensure(3 * (size_t)n));
     CU(c->in_radii.ensure(n));
     CU(c->out_sasa.ensure(n));
     cudaStream_t st = c->stream;
     const size_t in_bytes = 32 * (size_t)n, out_bytes = 8 * (size_t)n;
     const bool staged = in_bytes + out_bytes <= kStageMax;
-    const bool threaded = staged && in_bytes >= kParallelCopyBytes;  // big transfers: several host threads fill the staging buffer
+    const bool threaded = staged && in_bytes >= kParallelCopyBytes;  // big enough to wake the copy pool
     if (threaded) {
         if (ensure_stage(c, in_bytes + out_bytes)) return FSB200_FAIL;
         unsigned char *hx = c->h_stage, *hr = c->h_stage + 24 * (size_t)n;
-        parallel_over_bytes(n_struct, off.data(), [&](int k) {
-            parallel_memcpy(hx + 24 * (size_t)off[k], xyz[k], sizeof(double) * 3 * (size_t)n_atoms[k]);
-            parallel_memcpy(hr + 8 * (size_t)off[k], radii[k], sizeof(double) * (size_t)n_atoms[k]);
-        });
+        std::vector<CopyJob> jobs;
+        jobs.reserve(2 * (size_t)n_struct);
+        for (int k = 0; k < n_struct; ++k) {
+            jobs.push_back({hx + 24 * (size_t)off[k], xyz[k], sizeof(double) * 3 * (size_t)n_atoms[k]});
+            jobs.push_back({hr + 8 * (size_t)off[k], radii[k], sizeof(double) * (size_t)n_atoms[k]});
+        }
+        parallel_copy(jobs);
         CU(cudaMemcpyAsync(c->in_xyz.p, hx, 24 * (size_t)n, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(c->in_radii.p, hr, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
     } else if (staged) {
@@ -608,6 +658,7 @@ int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_ato
             CU(cudaMemcpyAsync(c->in_radii.p + off[k], radii[k], sizeof(double) * (size_t)n_atoms[k], cudaMemcpyHostToDevice, st));
         }
     }
+    const auto t_staged = std::chrono::steady_clock::now();
     Request rq{alg, resolution, probe, n, n_struct, off.data(), c->in_xyz.p, c->in_radii.p, c->out_sasa.p, nullptr, 0, 1, st};
     double *h_out = staged ? reinterpret_cast<double *>(c->h_stage + in_bytes) : nullptr;
     auto download = [&](cudaStream_t s) -> int {
@@ -620,10 +671,16 @@ int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_ato
         return FSB200_SUCCESS;
     };
     const int rc = run_pipeline(c, rq, download);
-    if (rc == FSB200_SUCCESS && threaded)
-        parallel_over_bytes(n_struct, off.data(), [&](int k) { parallel_memcpy(sasa[k], h_out + off[k], sizeof(double) * (size_t)n_atoms[k]); });
-    else if (rc == FSB200_SUCCESS && staged)
+    if (rc == FSB200_SUCCESS && threaded) {
+        std::vector<CopyJob> jobs;
+        jobs.reserve(n_struct);
+        for (int k = 0; k < n_struct; ++k) jobs.push_back({sasa[k], h_out + off[k], sizeof(double) * (size_t)n_atoms[k]});
+        parallel_copy(jobs);
+    } else if (rc == FSB200_SUCCESS && staged)
         for (int k = 0; k < n_struct; ++k) std::memcpy(sasa[k], h_out + off[k], sizeof(double) * (size_t)n_atoms[k]);
+    const auto t_end = std::chrono::steady_clock::now();
+    c->stats.host_stage_ms = std::chrono::duration<float, std::milli>(t_staged - t_begin).count();
+    c->stats.host_total_ms = std::chrono::duration<float, std::milli>(t_end - t_begin).count();
     return rc;
 }
 

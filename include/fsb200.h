@@ -56,6 +56,8 @@ typedef struct fsb200_stats {
     int kernel_launches;     /* kernels launched by this call */
     float device_ms;         /* device time of the call, CUDA events on the call's stream */
     float integrate_ms;      /* device time of the integration kernel alone */
+    float host_stage_ms;     /* host-pointer calls: wall time spent staging + enqueueing the upload */
+    float host_total_ms;     /* host-pointer calls: wall time of the whole call */
 } fsb200_stats;
 
 /* ---- library / device -------------------------------------------------------------------- */
