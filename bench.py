@@ -39,10 +39,10 @@ N_SLICES = 100
 PROBE = 1.4
 ALG_BYTES_PER_ATOM = 40.0
 # DRAM traffic of the dominant kernel, from the committed ncu --set full capture of this same command
-# (bench.py --steps 2 --warmup 3): 3.87 MB read + 0 B written per launch for 100k atoms = 38.7 B/atom,
-# i.e. the 32 B/atom sorted double4 records are fetched once and everything else stays in L2/shared memory.
-NCU_DRAM_BYTES_PER_LAUNCH = 3867904
-NCU_SOURCE = "profiles/r1_06_lr_ring_v2.txt"
+# (bench.py --steps 2 --warmup 3): 4.84 MB read + 0.0 KB written per launch for 100k atoms = 48.4 B/atom,
+# i.e. the 32 B/atom sorted double4 records are fetched about once and everything else stays in L2/shared memory.
+NCU_DRAM_BYTES_PER_LAUNCH = 4841984
+NCU_SOURCE = "profiles/r1_11_lr_certificate_v2.txt"
 METRIC = "atoms/sec (LR n_slices=100)"
 WORKLOAD = "C2: 100k-atom synthetic globular coord array, Lee-Richards n_slices=100, probe 1.4 A"
 

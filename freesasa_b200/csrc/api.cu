@@ -415,7 +415,7 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     fsb200_stats &s = c->stats;
     s.n_atoms = rq.n;
     s.n_structures = rq.n_struct;
-    s.n_items = c->h_status[kCtrItems];
+    s.n_items = c->h_status[kCtrItems] + c->h_status[kCtrItemsBack];
     s.n_overflow = c->h_status[kCtrOverflow];
     s.n_certified = c->h_status[kCtrCertified];
     s.max_neighbours = 0;

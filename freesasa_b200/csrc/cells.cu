@@ -244,7 +244,22 @@ __global__ void __launch_bounds__(256) k_reorder(Workspace ws)
         it.cell = cell - ws.grid[sid].cell_base;
         it.first = pos;
         it.count = min(kItemAtoms, end - pos);
-        ws.items[atomicAdd(ws.counters + kCtrItems, 1)] = it;
+        // Expensive work first: atoms of cells that touch empty space are the ones with exposed surface (they
+        // cannot be settled by the buried-atom certificate and cost ~10x more), so their items go to the FRONT
+        // of the queue and interior cells to the back; the kernel's tail then consists of cheap items.
+        const GridDesc &g = ws.grid[sid];
+        const int cx = it.cell % g.dim[0], cy = (it.cell / g.dim[0]) % g.dim[1], cz = it.cell / (g.dim[0] * g.dim[1]);
+        bool surface = false;
+        for (int dz = -1; dz <= 1 && !surface; ++dz)
+            for (int dy = -1; dy <= 1 && !surface; ++dy)
+                for (int dx = -1; dx <= 1 && !surface; ++dx) {
+                    const int x = cx + dx, y = cy + dy, z = cz + dz;
+                    if (x < 0 || y < 0 || z < 0 || x >= g.dim[0] || y >= g.dim[1] || z >= g.dim[2]) { surface = true; break; }
+                    const int c = g.cell_base + x + g.dim[0] * (y + g.dim[1] * z);
+                    surface = ws.cell_start[c + 1] == ws.cell_start[c];
+                }
+        if (surface) ws.items[atomicAdd(ws.counters + kCtrItems, 1)] = it;
+        else ws.items[ws.n - 1 - atomicAdd(ws.counters + kCtrItemsBack, 1)] = it;
     }
 }
 

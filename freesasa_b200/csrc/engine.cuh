@@ -52,7 +52,8 @@ struct Item {
 
 // Device-side counters / status of one call (one 64-int block, zeroed per call).
 enum CounterSlot {
-    kCtrItems = 0,      // number of work items produced by reorder
+    kCtrItems = 0,      // work items of surface cells (front of the item array)
+    kCtrItemsBack = 14, // work items of interior cells (stored from the back of the item array)
     kCtrQueue = 1,      // work queue head of the integration kernel
     kCtrOverflow = 2,   // atoms whose neighbour list did not fit kNbCap
     kCtrMaxCand = 3,    // max candidate count among overflow atoms

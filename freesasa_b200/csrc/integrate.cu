@@ -906,6 +906,7 @@ __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_c
 __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateArgs &args, int n_items, Slot *sl,
                                           double4 *tile, uint64_t *bar, int fill, int lane)
 {
+    const int n_front = ws.counters[kCtrItems];
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(ws.counters + kCtrQueue, 1);
@@ -921,7 +922,7 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
             }
             return;
         }
-        const Item it = ws.items[idx];
+        const Item it = ws.items[idx < n_front ? idx : ws.n - 1 - (idx - n_front)];   // surface cells first, then interior
         if (!(it.first < args.shard_end && it.first + it.count > args.shard_begin)) continue;  // another shard's
         const GridDesc &g = ws.grid[it.sid];
         const int cx = it.cell % g.dim[0], cy = (it.cell / g.dim[0]) % g.dim[1], cz = it.cell / (g.dim[0] * g.dim[1]);
@@ -978,7 +979,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     double4 *tiles = reinterpret_cast<double4 *>(smem);
     unsigned char *warp_mem = smem + (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
     const WarpMem<ALG, T> wm(warp_mem, kNbCap);
-    const int n_items = ws.counters[kCtrItems];
+    const int n_items = ws.counters[kCtrItems] + ws.counters[kCtrItemsBack];
     if (tid == 0) {
         cur = 0;
         for (int s = 0; s < kRingSlots; ++s) {
