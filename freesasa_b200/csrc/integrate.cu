@@ -885,7 +885,8 @@ __device__ __forceinline__ void cell_run(const Workspace &ws, const GridDesc &g,
 // before surface atoms; a first ring that refilled a slot only after every warp had LEFT it still left
 // 18 % of the samples (and 25 % of the issued instructions) in the mbarrier wait.
 struct Slot {
-    int claim;        // (fill & 0xffff) << 16 | next unclaimed atom
+    int claim;        // (fill & 0xffff) << 16 | n_atoms << 8 | next unclaimed atom: ONE word, so that "is there an
+                      // atom left in fill f" and the claim itself are decided on the same atomic snapshot
     int gathered;     // atoms of this fill whose neighbour gather is complete
     int n_atoms;      // atoms in the item (0 for a dead slot)
     int dead;         // the global queue was empty when this slot was last refilled: no more fills here
@@ -916,7 +917,7 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
                 sl->n_atoms = 0;
                 sl->dead = 1;
                 sl->gathered = 0;
-                sl->claim = (fill & 0xffff) << 16;
+                sl->claim = (fill & 0xffff) << 16;             // n_atoms = 0, next = 0
                 __threadfence_block();
                 mbar_arrive(bar);
             }
@@ -949,7 +950,7 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
             sl->total = total;
             sl->staged = staged ? 1 : 0;
             sl->self_off = off4 - b4;
-            sl->claim = (fill & 0xffff) << 16;
+            sl->claim = ((fill & 0xffff) << 16) | (it.count << 8);
         }
         __threadfence_block();
         __syncwarp();
@@ -1016,8 +1017,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
                 const unsigned gen = (unsigned)w >> 16;
                 if (gen == (unsigned)(f & 0xffff)) {
                     if (mbar_test(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u)) {
-                        a = w & 0xffff;
-                        if (a >= ld_volatile(&sl->n_atoms)) atomicCAS(&cur, f, f + 1);     // fill exhausted: open the next one
+                        a = w & 0xff;
+                        // (a fill's atom count travels in the claim word: reading it from the slot instead let a
+                        //  warp claim a non-existent atom of an exhausted one-atom fill whose slot was just being
+                        //  recycled — caught by the self-check below on 1024-structure batches)
+                        if (a >= ((w >> 8) & 0xff)) atomicCAS(&cur, f, f + 1);             // fill exhausted: open the next one
                         else if (atomicCAS(&sl->claim, w, w + 1) == w) code = 1;
                     }
                 } else if (((gen - (unsigned)f) & 0xffffu) < 0x8000u) {
@@ -1080,7 +1084,16 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         int g = 0;
         if (lane == 0) {
             __threadfence_block();
+            const int w_now = ld_volatile(&sl->claim);
             g = atomicAdd(&sl->gathered, 1) + 1;
+            // protocol self-check: the slot must still host my fill, and the count can never pass n_atoms
+            if (((unsigned)w_now >> 16) != (unsigned)(f & 0xffff) || g > n_atoms) {
+                if (atomicExch(ws.counters + kCtrStalled, 2) == 0) {
+                    int *dbg = ws.counters + 7;
+                    dbg[0] = f; dbg[1] = w_now; dbg[2] = g; dbg[3] = n_atoms * 2; dbg[4] = a; dbg[5] = sl->n_atoms; dbg[6] = pos;
+                    dbg[7] = -1; dbg[8] = ld_volatile(&cur);
+                }
+            }
         }
         g = __shfl_sync(kFull, g, 0);
         if (g == n_atoms) fill_slot(ws, args, n_items, sl, tile, &full[s], f + kRingSlots, lane);  // last gather: recycle the slot

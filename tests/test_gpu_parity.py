@@ -177,6 +177,28 @@ def test_ragged_batch_with_tiny_structures(eng32):
             assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
 
 
+def test_many_tiny_work_items_stress(eng32):
+    """Hundreds of small and sparse structures in one pass: most work items hold one or two atoms, so the
+    kernel's tile ring turns over thousands of times per CTA.  (Regression: a warp could claim a non-existent
+    atom of an exhausted one-atom item whose slot was being recycled; results then varied from run to run.)"""
+    rng = np.random.default_rng(21)
+    structs = []
+    for k in range(400):
+        n = int(rng.integers(20, 260))
+        if k % 3 == 0:   # sparse: atoms mostly alone in their cells
+            structs.append((rng.uniform(-40, 40, (n, 3)), rng.choice([1.5, 1.8], n)))
+        else:
+            structs.append(fs.workloads.globule(n, seed=1000 + k, offset=rng.uniform(-200, 200, 3)))
+    for alg, res, tol in [(0, 12, LR_TOL_FP32), (1, 60, SR_TOL)]:
+        first = eng32.calc_batch(alg, structs, 1.4, res)
+        for rep in range(3):
+            again = eng32.calc_batch(alg, structs, 1.4, res)
+            for a, b in zip(first, again):
+                np.testing.assert_array_equal(a, b)
+        for (x, r), got in zip(structs, first):
+            assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
+
+
 def test_large_probe_and_radii(eng32):
     """Probe and radii far outside the protein range: many more neighbours per atom, coarse grid."""
     x, r = fs.workloads.globule(900, seed=5)
