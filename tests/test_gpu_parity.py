@@ -177,6 +177,20 @@ def test_ragged_batch_with_tiny_structures(eng32):
             assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
 
 
+def test_dense_packing_uses_the_wide_paths(eng32, eng64):
+    """Twice the protein density (as with explicit hydrogens): 97..160 neighbours take the keyed all-arcs path,
+    more than 160 the global-memory overflow kernel; both must agree with the oracle like the common path."""
+    x, r = fs.workloads.globule(4000, seed=13)
+    x = x * 0.78
+    start, _ = ob.oracle_neighbours(x, r + 1.4)
+    nn = np.diff(start)
+    assert (nn > 96).mean() > 0.3 and nn.max() > 120
+    for alg, res, tol in [(0, 24, LR_TOL_FP32), (1, 150, SR_TOL)]:
+        assert maxerr(eng32.calc(alg, x, r, 1.4, res), ob.oracle_calc(x, r, alg, 1.4, res)) < tol
+    assert maxerr(eng64.calc(0, x, r, 1.4, 24), ob.oracle_calc(x, r, 0, 1.4, 24)) < LR_TOL_FP64
+    np.testing.assert_array_equal(eng32.neighbour_counts(x, r, 1.4), nn)
+
+
 def test_many_tiny_work_items_stress(eng32):
     """Hundreds of small and sparse structures in one pass: most work items hold one or two atoms, so the
     kernel's tile ring turns over thousands of times per CTA.  (Regression: a warp could claim a non-existent
