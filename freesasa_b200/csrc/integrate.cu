@@ -730,30 +730,39 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     const unsigned lt = lanemask_lt();
     int n_useful = 0;
     bool inside = false;
-    for (int base = 0; base < nn; base += 32) {
-        const int j = base + lane;
-        float4 e = make_float4(0.f, 0.f, 0.f, 3.0e38f);
-        bool useful = false;
-        if (j < nn) {
-            const Rec4<T> r = recs[j];
-            e.x = (float)r.a; e.y = (float)r.b; e.z = (float)r.c;
-            const float d2 = e.x * e.x + e.y * e.y + e.z * e.z;
-            const float d = sqrtf(d2);
-            const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
-            if (t < -d - 1e-4f * (d + Ri)) inside = true;  // sphere i lies strictly inside sphere a (coincident equal
-                                                           // spheres, t = d = 0, do NOT count: the reference decides
-                                                           // their points one rounding at a time)
-            else if (t < d * kCertCos) {                   // cap wider than a patch
-                e.w = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
-                useful = true;
+    // Short list = neighbours whose cap is wider than a patch.  If more than kCertList qualify (dense packing,
+    // explicit hydrogens), the bar is raised to caps at least 20, 35, 50 degrees wider, until they fit: the
+    // widest caps are the ones that hide whole patches anyway.
+    const float bars[4] = {kCertCos, 0.82412619f, 0.64944805f, 0.43051110f};   // cos(14.5, 34.5, 49.5, 64.5 deg)
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        const float bar = bars[attempt];
+        n_useful = 0;
+        for (int base = 0; base < nn; base += 32) {
+            const int j = base + lane;
+            float4 e = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+            bool useful = false;
+            if (j < nn) {
+                const Rec4<T> r = recs[j];
+                e.x = (float)r.a; e.y = (float)r.b; e.z = (float)r.c;
+                const float d2 = e.x * e.x + e.y * e.y + e.z * e.z;
+                const float d = sqrtf(d2);
+                const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
+                if (t < -d - 1e-4f * (d + Ri)) inside = true;  // sphere i lies strictly inside sphere a (coincident equal
+                                                               // spheres, t = d = 0, do NOT count: the reference decides
+                                                               // their points one rounding at a time)
+                else if (t < d * bar) {                        // cap wide enough for this attempt
+                    e.w = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
+                    useful = true;
+                }
             }
+            const unsigned m = __ballot_sync(kFull, useful);
+            if (useful) {
+                const int slot = n_useful + __popc(m & lt);
+                if (slot < kCertList) list[slot] = e;
+            }
+            n_useful += __popc(m);
         }
-        const unsigned m = __ballot_sync(kFull, useful);
-        if (useful) {
-            const int slot = n_useful + __popc(m & lt);
-            if (slot < kCertList) list[slot] = e;
-        }
-        n_useful += __popc(m);
+        if (n_useful <= kCertList) break;
     }
     if (__any_sync(kFull, inside)) return true;
     if (n_useful == 0 || n_useful > kCertList) return false;   // nothing to work with / too many for the short list
