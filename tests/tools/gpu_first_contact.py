@@ -1,7 +1,7 @@
 """First-contact script for the GPU box: prints errors instead of asserting, writes gpurun_out/debug.json."""
 import json, os, sys, time, traceback
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in scripts/)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import freesasa_b200 as fs
 from oracle import bindings as ob

@@ -1,7 +1,7 @@
 """Measure every BASELINE.json configuration on ONE GPU (C4/C5 are 8-GPU configs; here their
 single-GPU time, which bench.py --gpus N scales by sharding).  Writes gpurun_out/configs.json.
 
-    python scripts/measure_configs.py [--skip-oracle]
+    python tests/tools/measure_configs.py [--skip-oracle]
 """
 import json
 import os
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import freesasa_b200 as fs  # noqa: E402
 from freesasa_b200 import workloads  # noqa: E402

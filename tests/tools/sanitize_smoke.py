@@ -1,12 +1,12 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck):
-    compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py
+    compute-sanitizer --tool memcheck python tests/tools/sanitize_smoke.py
 Covers both integrators, both precisions, a batch, the crowded (overflow + unstaged) path and sharding."""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import freesasa_b200 as fs  # noqa: E402
 
 rng = np.random.default_rng(0)
