@@ -512,10 +512,9 @@ __device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
 
 template <int K>
 __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
-                                                double Ri_d, int ns, float band_lo, float band_hi, int lane)
+                                                double Ri_d, int ns, int lane)
 {
     const float Ri = (float)Ri_d;
-    const float z_lo = band_lo * Ri, z_hi = band_hi * Ri;  // slices outside are certainly covered (see certify_buried)
     const double delta = 2.0 * Ri_d / ns;
     const unsigned lt = lanemask_lt();
     Rec4<float> r[K];                                      // this lane's K records, for all slices of the atom
@@ -529,7 +528,6 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
 
     for (int s = 0; s < ns; ++s) {
         const float zr = (float)(-Ri_d + (s + 0.5) * delta);
-        if (zr < z_lo || zr > z_hi) continue;              // proved covered by the direction probe
         const float az = fabsf(zr);
         const float a2 = (Ri - az) * (Ri + az);
         if (!(a2 > 0.f)) continue;
@@ -727,13 +725,8 @@ __constant__ float4 c_cert_points[kCertPoints];   // the probe directions (uploa
 // load — is tested against all of them at once and a single vote says whether some neighbour hides its whole
 // patch.  The first patch nobody hides ends the attempt.
 template <typename T, bool HAS_T>   // HAS_T: recs hold {dx,dy,dz,t} (S&R); otherwise raw {dx,dy,dz,Ra} (L&R)
-__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list, int nn, float Ri, int lane,
-                                               float *band_lo, float *band_hi)
+__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list, int nn, float Ri, int lane)
 {
-    // Latitude band (in z of the unit sphere) outside which every Lee-Richards slice is certainly covered;
-    // the whole sphere unless the directions were all examined.
-    *band_lo = -1.f;
-    *band_hi = 1.f;
     const unsigned lt = lanemask_lt();
     int n_useful = 0;
     bool inside = false;
@@ -778,32 +771,21 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     const float4 n0 = lane < n_useful ? list[lane] : none;
     const float4 n1 = lane + 32 < n_useful ? list[lane + 32] : none;
     __syncwarp();                                              // the list's memory is reused by the integrators
-    // Not an early exit at the first unhidden patch: the z-range of the unhidden directions is worth having.
-    // A slice circle at latitude phi can only touch patches whose centre lies within rho of phi, so a slice whose
-    // latitude is more than rho away from EVERY unhidden direction is completely covered (same argument as for the
-    // whole sphere) and need not be integrated: an atom exposed only on one side skips the slices of the other.
-    float z_min = 2.f, z_max = -2.f;
     if (n_useful <= 32) {
         for (int k = 0; k < kCertPoints; ++k) {
             const float4 u = c_cert_points[k];                 // uniform address: constant-cache broadcast
             const bool c = fmaf(u.x, n0.x, fmaf(u.y, n0.y, u.z * n0.z)) >= n0.w;
-            if (!__any_sync(kFull, c)) { z_min = fminf(z_min, u.z); z_max = fmaxf(z_max, u.z); }
+            if (!__any_sync(kFull, c)) return false;
         }
     } else {
         for (int k = 0; k < kCertPoints; ++k) {
             const float4 u = c_cert_points[k];
             const bool c = fmaf(u.x, n0.x, fmaf(u.y, n0.y, u.z * n0.z)) >= n0.w ||
                            fmaf(u.x, n1.x, fmaf(u.y, n1.y, u.z * n1.z)) >= n1.w;
-            if (!__any_sync(kFull, c)) { z_min = fminf(z_min, u.z); z_max = fmaxf(z_max, u.z); }
+            if (!__any_sync(kFull, c)) return false;
         }
     }
-    if (z_min > z_max) return true;                            // every patch hidden: the atom is buried
-    // sin(lat -/+ rho) = z cos(rho) -/+ sqrt(1 - z^2) sin(rho), valid while lat -/+ rho stays inside (-90, 90) deg
-    const float c_lo = sqrtf(fmaxf(1.f - z_min * z_min, 0.f)), c_hi = sqrtf(fmaxf(1.f - z_max * z_max, 0.f));
-    // (the guards are cos(lat_min - rho) > 0 and cos(lat_max + rho) > 0: otherwise the band reaches the pole)
-    *band_lo = (c_lo * kCertCos + z_min * kCertSin > 0.f) ? z_min * kCertCos - c_lo * kCertSin - 1e-4f : -1.f;
-    *band_hi = (c_hi * kCertCos - z_max * kCertSin > 0.f) ? z_max * kCertCos + c_hi * kCertSin + 1e-4f : 1.f;
-    return false;
+    return true;
 }
 
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
@@ -839,11 +821,10 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
     }
     double area = 0.0;
     bool certified = false;
-    float band_lo = -1.f, band_hi = 1.f;                   // z-range (unit sphere) of the slices that need integrating
     if (s.R > 0.0) {
         if constexpr (FAST && sizeof(T) == 4) {
             if (args.cert_points != nullptr && nn > 0)
-                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_list, nn, (float)s.R, lane, &band_lo, &band_hi);
+                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_list, nn, (float)s.R, lane);
         }
         if (certified) {
             // area stays 0: proved completely buried
@@ -854,7 +835,7 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
                 float *starts = reinterpret_cast<float *>(wm.starts);
                 if (nn <= 96) {                            // ONE instantiation (K = 3) for all of them: the kernel is
                     lr_prepare_sorted<3>(recs, nn, lane);  // instruction-cache sensitive (ncu: no_instruction stalls
-                    area = lr_atom_fastk<3>(recs, arcs, starts, nn, s.R, args.resolution, band_lo, band_hi, lane);  // with K = 1, 2, 3 side by side)
+                    area = lr_atom_fastk<3>(recs, arcs, starts, nn, s.R, args.resolution, lane);  // with K = 1, 2, 3 side by side)
                 } else {
                     lr_prepare<float>(recs, nn, lane);
                     area = lr_atom_fast(recs, arcs, starts, nn, s.R, args.resolution, lane);
