@@ -761,6 +761,16 @@ int fsb200_ctx_unpermute(fsb200_ctx *c, const double *d_sorted, double *d_out, i
     return FSB200_SUCCESS;
 }
 
+int fsb200_test_points(int n_points, double *out)
+{
+    if (n_points <= 0 || !out) return fail("invalid arguments");
+    std::vector<double> pd;
+    std::vector<float4> pf;
+    make_test_points(n_points, pd, pf);
+    std::memcpy(out, pd.data(), pd.size() * sizeof(double));
+    return FSB200_SUCCESS;
+}
+
 // ---- context-free drop-in entry points ------------------------------------------------------------------
 int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
                       double *const *sasa, double probe, int resolution)

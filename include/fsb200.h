@@ -123,6 +123,10 @@ int fsb200_ctx_unpermute(fsb200_ctx *ctx, const double *d_sorted, double *d_out,
  * settled by the buried-atom certificate. */
 int fsb200_ctx_neighbour_counts(fsb200_ctx *ctx, int *counts, const double *xyz, const double *radii,
                                 int n, double probe);
+/* The n Shrake-Rupley unit test points exactly as the engine hands them to the device (3n doubles): the
+ * reference's golden spiral (src/sasa_sr.c:56-90), bit-identical values, in the engine's patch order.
+ * Pure host code: works without a GPU. */
+int fsb200_test_points(int n_points, double *out);
 
 #ifdef __cplusplus
 }

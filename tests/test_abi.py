@@ -1,6 +1,7 @@
 """CPU tests: the C-ABI libraries load and export every symbol the headers declare; host-side
 validation mirrors the reference (no compute without a GPU)."""
 import ctypes
+import math
 import os
 import re
 
@@ -80,6 +81,24 @@ def test_parameter_validation_like_reference(built, capfd):
     assert not H.freesasa_calc_coord(xyz.ctypes.data_as(dp), rad.ctypes.data_as(dp), 1, ctypes.byref(bad))
     assert capfd.readouterr().err == ""
     H.freesasa_set_verbosity(0)
+
+
+@pytest.mark.parametrize("n", [1, 31, 100, 128, 1000, 4999])
+def test_engine_test_points_are_the_reference_points_reordered(built, n):
+    """The engine tests Shrake-Rupley points in patch order; the SET must be the reference's golden spiral,
+    bit for bit (the count of exposed points does not depend on the order).  Host code: no GPU needed."""
+    from oracle import bindings as ob
+
+    lib = ctypes.CDLL(built["engine"])
+    lib.fsb200_test_points.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    out = np.empty((n, 3))
+    assert lib.fsb200_test_points(n, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+    want = ob.oracle_test_points(n)  # pinned to the reference in tests/test_oracle.py
+    key = lambda a: a[np.lexsort((a[:, 0], a[:, 1], a[:, 2]))]
+    np.testing.assert_array_equal(key(out), key(want))
+    if n >= 64:  # consecutive groups of 32 are compact patches: far smaller than the sphere
+        spans = [np.linalg.norm(out[i : i + 32] - out[i : i + 32].mean(0), axis=1).max() for i in range(0, n - 31, 32)]
+        assert np.median(spans) < 3.2 * math.sqrt(4 * math.pi * 32 / n) / 2 + 0.05
 
 
 def test_no_cpu_fallback(built):
