@@ -213,6 +213,45 @@ def test_many_tiny_work_items_stress(eng32):
             assert maxerr(got, ob.oracle_calc(x, r, alg, 1.4, res)) < tol
 
 
+def test_concurrent_callers(synthetic_fixtures):
+    """The reference library is re-entrant (doc/doxy-main.md:741-756); so must the drop-in be: several host threads
+    call freesasa_calc_coord at once (ctypes releases the GIL), each gets a context from the pool."""
+    import threading
+
+    f = synthetic_fixtures
+    x, r = f["g3000_xyz"], f["g3000_radii"]
+    big_x, big_r = fs.workloads.globule(300000, seed=5)   # large enough to wake the host copy pool
+    want_big = None
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(6):
+                if k % 2 == 0:
+                    got = fs.calc_coord(x, r, params(fs.LEE_RICHARDS, 20)).sasa
+                    assert maxerr(got, f["g3000_lr20"]) < LR_TOL_FP32
+                else:
+                    got = fs.calc_coord(x + 0.5 * k, r, params(fs.SHRAKE_RUPLEY, 100)).sasa
+                    assert maxerr(got, f["g3000_sr100"]) < SR_TOL
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def big_worker():
+        try:
+            a = fs.calc_coord(big_x, big_r, params(fs.SHRAKE_RUPLEY, 60)).sasa
+            b = fs.calc_coord(big_x, big_r, params(fs.SHRAKE_RUPLEY, 60)).sasa
+            np.testing.assert_array_equal(a, b)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)] + [threading.Thread(target=big_worker) for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_large_probe_and_radii(eng32):
     """Probe and radii far outside the protein range: many more neighbours per atom, coarse grid."""
     x, r = fs.workloads.globule(900, seed=5)
