@@ -220,6 +220,7 @@ def test_concurrent_callers(synthetic_fixtures):
 
     f = synthetic_fixtures
     x, r = f["g3000_xyz"], f["g3000_radii"]
+    want_lr, want_sr = f["g3000_lr20"], f["g3000_sr100"]   # (NpzFile is not thread-safe: load before the threads start)
     big_x, big_r = fs.workloads.globule(300000, seed=5)   # large enough to wake the host copy pool
     want_big = None
     errors = []
@@ -229,10 +230,10 @@ def test_concurrent_callers(synthetic_fixtures):
             for rep in range(6):
                 if k % 2 == 0:
                     got = fs.calc_coord(x, r, params(fs.LEE_RICHARDS, 20)).sasa
-                    assert maxerr(got, f["g3000_lr20"]) < LR_TOL_FP32
+                    assert maxerr(got, want_lr) < LR_TOL_FP32
                 else:
                     got = fs.calc_coord(x + 0.5 * k, r, params(fs.SHRAKE_RUPLEY, 100)).sasa
-                    assert maxerr(got, f["g3000_sr100"]) < SR_TOL
+                    assert maxerr(got, want_sr) < SR_TOL
         except Exception as e:  # noqa: BLE001
             errors.append(repr(e))
 
