@@ -12,7 +12,7 @@
  * What changes: the numeric work is one call into the GPU engine; n_threads is validated but does
  * not drive anything.  There is no CPU fallback: if the engine fails, the message says why.
  */
-#include "freesasa_b200_host.h"
+#include "host_internal.h"
 #include "fsb200.h"
 
 #include <assert.h>
@@ -46,7 +46,7 @@ void freesasa_set_err_out(FILE *fp)
 }
 FILE *freesasa_get_err_out(void) { return errlog; }
 
-static int report(int code, const char *where, int line, const char *fmt, ...)
+int fsb_report(int code, const char *where, int line, const char *fmt, ...)
 {
     va_list ap;
     FILE *fp = errlog ? errlog : stderr;
@@ -63,8 +63,6 @@ static int report(int code, const char *where, int line, const char *fmt, ...)
     fflush(fp);
     return code;
 }
-#define FAIL_MSG(...) report(FREESASA_FAIL, __FILE__, __LINE__, __VA_ARGS__)
-#define WARN_MSG(...) report(FREESASA_WARN, NULL, 0, __VA_ARGS__)
 
 /* shared validation of src/sasa_lr.c:169-193 / src/sasa_sr.c:173-200; returns 1 if the caller should
  * return *rc immediately */
@@ -156,7 +154,7 @@ freesasa_result *freesasa_calc(const coord_t *c, const double *radii, const free
     assert(radii);
     result = result_new(c->n);
     if (result == NULL) {
-        FAIL_MSG("");
+        FAIL_MSG("%s", "");
         return NULL;
     }
     if (parameters == NULL) parameters = &freesasa_default_parameters;
@@ -190,7 +188,7 @@ freesasa_result *freesasa_calc_coord(const double *xyz, const double *radii, int
     view.is_linked = 1;
     view.xyz = (double *)xyz;
     result = freesasa_calc(&view, radii, parameters);
-    if (result == NULL) FAIL_MSG("");
+    if (result == NULL) FAIL_MSG("%s", "");
     return result;
 }
 

@@ -1,0 +1,981 @@
+/* freesasa_b200/csrc/ingest.c — PDB text -> structure (coordinates, radii, labels) for the SASA engine.
+ *
+ * Scope row f-1 of SURVEY.md §8(f): once the calculation takes ~1 ms, reading the input dominates (the reference
+ * needs 92 ms to read the 13 928 atoms of 2isk).  This file provides the reference's structure API
+ * (src/freesasa.h:749-1446) with the same observable behaviour as src/structure.c + src/pdb.c, on a different
+ * machine model:
+ *
+ *   reference                                            here
+ *   ---------------------------------------------------  ------------------------------------------------------
+ *   fgets() per line, ftell() per line                   the byte range is read with ONE fread; lines are slices
+ *   malloc(struct atom) + strdup(line) per atom,         structure-of-arrays with geometric growth: xyz, radius,
+ *   realloc of the pointer arrays every 512 atoms         fixed-width label records, one arena for the PDB lines
+ *   3 classifier searches per atom, each malloc +         one hashed lookup per atom (radii.c)
+ *   sscanf + linear strcmp scans
+ *   sscanf("%lf%lf%lf") for the coordinates              exact decimal fast path (integer mantissa / power of ten,
+ *                                                        one correctly rounded division == strtod), sscanf only for
+ *                                                        exotic tokens (exponents, hex, inf/nan, > 15 digits)
+ *   linear scan over all chains per atom                 previous atom's chain first
+ *
+ * Everything observable is kept, including the quirks: which lines count as atoms (src/structure.c:662-666), the
+ * hydrogen test that only fires on lines long enough to carry an element symbol (src/pdb.c:260-283), "first
+ * alternate location wins" (src/structure.c:672-679), residue = change of residue number or chain between
+ * consecutive atoms (src/structure.c:484-496), chain = first appearance of a label (src/structure.c:459-478),
+ * MODEL/ENDMDL handling, the file-range arithmetic of freesasa_structure_array(), messages and return codes.
+ * The coordinates and radii are bit-identical to the reference's (tests/test_ingest.py).
+ */
+#include "host_internal.h"
+
+#include <assert.h>
+#include <errno.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define LINE_MAX_STRL 120 /* PDB_MAX_LINE_STRL, src/pdb.h:22: fgets() buffer of the reference, longer lines are split */
+
+int fsb_classifier_row(const freesasa_classifier *c, const char *res_name, const char *atom_name);
+double fsb_classifier_row_radius(const freesasa_classifier *c, int row);
+int fsb_classifier_row_class(const freesasa_classifier *c, int row);
+
+/* the bytes a set of structures was read from, shared by reference count (freesasa_structure_array() makes several
+ * structures from one file) */
+struct shared_text {
+    char *data;
+    long len;
+    int refs;
+};
+static void text_release(struct shared_text *t)
+{
+    if (t && __atomic_sub_fetch(&t->refs, 1, __ATOMIC_ACQ_REL) == 0) {
+        free(t->data);
+        free(t);
+    }
+}
+
+/* fixed-width, NUL-terminated label fields of one atom (widths: src/pdb.h:17-20, src/structure.c:30-32) */
+struct atom_label {
+    char name[5];
+    char res_name[4];
+    char res_number[6];
+    char symbol[3];
+    char chain[4];
+};
+
+struct freesasa_structure {
+    int n, cap;
+    coord_t coord; /* coord.xyz owned, 3*cap doubles; what freesasa_calc() receives */
+    double *radius;
+    struct atom_label *label;
+    int *res_index;
+    unsigned char *cls;
+    /* PDB lines are not copied while reading: the structure keeps a reference to the text it was read from and a
+     * slice per atom; NUL-terminated copies are made only if somebody asks for them (atom_pdb_line) */
+    struct shared_text *text;
+    long *line_at;           /* offset into text->data, -1 = the atom did not come from a PDB line */
+    unsigned char *line_len; /* <= 119 */
+    char *volatile lines;    /* lazily built: n strings of stride LINE_MAX_STRL */
+    /* residues */
+    int n_res, cap_res;
+    int *res_first;
+    freesasa_nodearea *res_ref;
+    unsigned char *res_has_ref;
+    /* chains, in order of first appearance */
+    int n_chains, cap_chains;
+    char (*chain_label)[4];
+    char *short_labels;
+    int *chain_first;
+    char *classifier_name;
+    const freesasa_classifier *last_classifier; /* classifier of the previous add: skips re-registering its name */
+    int model;
+};
+
+/* ---- storage ---------------------------------------------------------------------------------------- */
+static int reserve_atoms(freesasa_structure *s, int cap)
+{
+    void *p;
+    if (cap <= s->cap) return FREESASA_SUCCESS;
+#define GROW(field, bytes)                                \
+    if (!(p = realloc(s->field, (size_t)cap * (bytes)))) return MEM_FAIL(); \
+    s->field = p
+    GROW(coord.xyz, 3 * sizeof(double));
+    GROW(radius, sizeof(double));
+    GROW(label, sizeof(struct atom_label));
+    GROW(res_index, sizeof(int));
+    GROW(cls, 1);
+    GROW(line_at, sizeof(long));
+    GROW(line_len, 1);
+#undef GROW
+    s->cap = cap;
+    return FREESASA_SUCCESS;
+}
+
+freesasa_structure *freesasa_structure_new(void)
+{
+    freesasa_structure *s = calloc(1, sizeof *s);
+    if (s == NULL) {
+        MEM_FAIL();
+        return NULL;
+    }
+    s->model = 1;
+    s->coord.is_linked = 0;
+    return s;
+}
+
+void freesasa_structure_free(freesasa_structure *s)
+{
+    if (s == NULL) return;
+    free(s->coord.xyz);
+    free(s->radius);
+    free(s->label);
+    free(s->res_index);
+    free(s->cls);
+    free(s->line_at);
+    free(s->line_len);
+    free(s->lines);
+    text_release(s->text);
+    free(s->res_first);
+    free(s->res_ref);
+    free(s->res_has_ref);
+    free(s->chain_label);
+    free(s->short_labels);
+    free(s->chain_first);
+    free(s->classifier_name);
+    free(s);
+}
+
+/* ---- adding one atom (structure_add_atom(), src/structure.c:568-631) ------------------------------------------ */
+static void copy_field(char *dst, size_t cap, const char *src)
+{
+    size_t n = strlen(src);
+    if (n >= cap) n = cap - 1; /* snprintf(dst, cap, "%s", src) of the reference */
+    memcpy(dst, src, n);
+    dst[n] = '\0';
+}
+
+/* guess_symbol(), src/structure.c:419-445; characters past the end of a short name read as NUL */
+static int guess_symbol(char symbol[3], const char *name)
+{
+    char n4[4] = {0, 0, 0, 0};
+    int i;
+    for (i = 0; i < 4 && name[i]; ++i) n4[i] = name[i];
+    if (n4[0] == ' ' || (n4[0] >= '1' && n4[0] <= '9')) {
+        symbol[0] = ' ';
+        symbol[1] = n4[1];
+        symbol[2] = '\0';
+    } else if (n4[3] == ' ') {
+        symbol[0] = n4[0];
+        symbol[1] = n4[0] ? n4[1] : '\0';
+        symbol[2] = '\0';
+    } else {
+        symbol[0] = ' ';
+        symbol[1] = n4[0];
+        symbol[2] = '\0';
+        return WARN_MSG("guessing that atom '%s' is symbol '%s'", name, symbol);
+    }
+    return FREESASA_SUCCESS;
+}
+
+static int register_classifier(freesasa_structure *s, const freesasa_classifier *classifier)
+{
+    const char *name = freesasa_classifier_name(classifier);
+    if (s->last_classifier == classifier && s->classifier_name) return FREESASA_SUCCESS;
+    s->last_classifier = classifier;
+    if (s->classifier_name == NULL) {
+        if (!(s->classifier_name = strdup(name))) return MEM_FAIL();
+    } else if (strcmp(s->classifier_name, name) != 0) {
+        free(s->classifier_name);
+        if (!(s->classifier_name = strdup(FREESASA_CONFLICTING_CLASSIFIERS))) return MEM_FAIL();
+        return FREESASA_WARN;
+    }
+    return FREESASA_SUCCESS;
+}
+
+/* Returns FREESASA_SUCCESS (atom stored), FREESASA_WARN (atom skipped) or FREESASA_FAIL. */
+#define ROW_UNSET (-2)
+static int add_atom(freesasa_structure *s, const struct atom_label *a, const double xyz[3],
+                    const freesasa_classifier *classifier, int options, const char *line, size_t line_len, int row)
+{
+    /* `a` is zero-padded (label fields compare with memcmp); `line` (optional) points into s->text; `row` is the
+     * classifier row of the atom if the caller already knows it, else ROW_UNSET */
+    int i;
+    double r;
+
+    if ((options & FREESASA_SKIP_UNKNOWN) && (options & FREESASA_HALT_AT_UNKNOWN)) options &= ~FREESASA_SKIP_UNKNOWN;
+    if (classifier == NULL) classifier = &freesasa_default_classifier;
+    if (s->last_classifier != classifier || !s->classifier_name) register_classifier(s, classifier);
+
+    if (row == ROW_UNSET) row = fsb_classifier_row(classifier, a->res_name, a->name);
+    if (options & FREESASA_RADIUS_FROM_OCCUPANCY) {
+        r = 1; /* replaced by the caller */
+    } else if (row >= 0) {
+        r = fsb_classifier_row_radius(classifier, row);
+    } else if (options & FREESASA_HALT_AT_UNKNOWN) {
+        FAIL_MSG("atom '%s %s' unknown", a->res_name, a->name);
+        return FAIL_MSG("halting at unknown atom");
+    } else if (options & FREESASA_SKIP_UNKNOWN) {
+        return WARN_MSG("skipping unknown atom '%s %s'", a->res_name, a->name);
+    } else {
+        r = freesasa_guess_radius(a->symbol);
+        if (r < 0) {
+            r = +0.;
+            WARN_MSG("atom '%s %s' unknown and can't guess radius of symbol '%s', assigning radius 0 A", a->res_name,
+                     a->name, a->symbol);
+        } else {
+            WARN_MSG("atom '%s %s' unknown, guessing element is '%s', and radius %.3f A", a->res_name, a->name, a->symbol, r);
+        }
+    }
+
+    if (s->n == s->cap && reserve_atoms(s, s->cap ? 2 * s->cap : 1024)) return FAIL_MSG("%s", "");
+    i = s->n;
+    s->coord.xyz[3 * i] = xyz[0];
+    s->coord.xyz[3 * i + 1] = xyz[1];
+    s->coord.xyz[3 * i + 2] = xyz[2];
+
+    /* new chain?  (structure_add_chain(), src/structure.c:459-478: a label is registered the first time it is seen) */
+    if (i == 0 || memcmp(a->chain, s->label[i - 1].chain, sizeof a->chain) != 0) {
+        int k, known = 0;
+        for (k = 0; k < s->n_chains && !known; ++k) known = strncmp(s->chain_label[k], a->chain, 4) == 0;
+        if (!known) {
+            if (s->n_chains == s->cap_chains) {
+                const int cap = s->cap_chains ? 2 * s->cap_chains : 64;
+                void *p;
+                if (!(p = realloc(s->chain_label, (size_t)cap * 4))) return MEM_FAIL();
+                s->chain_label = p;
+                if (!(p = realloc(s->short_labels, (size_t)cap + 1))) return MEM_FAIL();
+                s->short_labels = p;
+                if (!(p = realloc(s->chain_first, (size_t)cap * sizeof(int)))) return MEM_FAIL();
+                s->chain_first = p;
+                s->cap_chains = cap;
+            }
+            memcpy(s->chain_label[s->n_chains], a->chain, 4);
+            s->short_labels[s->n_chains] = a->chain[0];
+            s->short_labels[s->n_chains + 1] = '\0';
+            s->chain_first[s->n_chains] = i;
+            ++s->n_chains;
+        }
+    }
+    /* new residue?  (structure_add_residue(), src/structure.c:480-516) */
+    if (s->n_res == 0 || (i > 0 && (memcmp(a->res_number, s->label[i - 1].res_number, sizeof a->res_number) ||
+                                    memcmp(a->chain, s->label[i - 1].chain, sizeof a->chain)))) {
+        const freesasa_nodearea *ref;
+        if (s->n_res == s->cap_res) {
+            const int cap = s->cap_res ? 2 * s->cap_res : 256;
+            void *p;
+            if (!(p = realloc(s->res_first, (size_t)cap * sizeof(int)))) return MEM_FAIL();
+            s->res_first = p;
+            if (!(p = realloc(s->res_ref, (size_t)cap * sizeof(freesasa_nodearea)))) return MEM_FAIL();
+            s->res_ref = p;
+            if (!(p = realloc(s->res_has_ref, (size_t)cap))) return MEM_FAIL();
+            s->res_has_ref = p;
+            s->cap_res = cap;
+        }
+        s->res_first[s->n_res] = i;
+        ref = freesasa_classifier_residue_reference(classifier, a->res_name);
+        s->res_has_ref[s->n_res] = ref != NULL;
+        if (ref) s->res_ref[s->n_res] = *ref;
+        ++s->n_res;
+    }
+    s->label[i] = *a;
+    s->cls[i] = (unsigned char)(row >= 0 ? fsb_classifier_row_class(classifier, row) : FREESASA_ATOM_UNKNOWN);
+    s->res_index[i] = s->n_res - 1;
+    s->radius[i] = r;
+    s->line_at[i] = line ? line - s->text->data : -1;
+    s->line_len[i] = (unsigned char)line_len;
+    s->n = i + 1;
+    s->coord.n = s->n;
+    return FREESASA_SUCCESS;
+}
+
+/* structure_add_atom_wopt_impl(), src/structure.c:723-767 */
+static int add_atom_wopt(freesasa_structure *s, const char *atom_name, const char *residue_name, const char *residue_number,
+                         const char *symbol, const char *chain_label, double x, double y, double z,
+                         const freesasa_classifier *classifier, int options)
+{
+    struct atom_label a;
+    const double v[3] = {x, y, z};
+    char my_symbol[3] = {0, 0, 0};
+    int ret, warn = 0;
+
+    assert(s);
+    assert(atom_name);
+    assert(residue_name);
+    assert(residue_number);
+    assert(chain_label);
+
+    memset(&a, 0, sizeof a);
+    options &= ~FREESASA_RADIUS_FROM_OCCUPANCY; /* cannot be used here */
+    if (symbol != NULL)
+        copy_field(my_symbol, sizeof my_symbol, symbol);
+    else if (guess_symbol(my_symbol, atom_name) == FREESASA_WARN && (options & FREESASA_SKIP_UNKNOWN))
+        ++warn;
+    copy_field(a.name, sizeof a.name, atom_name);
+    copy_field(a.res_name, sizeof a.res_name, residue_name);
+    copy_field(a.res_number, sizeof a.res_number, residue_number);
+    copy_field(a.symbol, sizeof a.symbol, my_symbol);
+    copy_field(a.chain, sizeof a.chain, chain_label);
+    ret = add_atom(s, &a, v, classifier, options, NULL, 0, ROW_UNSET);
+    if (!ret && warn) return FREESASA_WARN;
+    return ret;
+}
+
+int freesasa_structure_add_atom_wopt(freesasa_structure *structure, const char *atom_name, const char *residue_name,
+                                     const char *residue_number, char chain_label, double x, double y, double z,
+                                     const freesasa_classifier *classifier, int options)
+{
+    const char label[2] = {chain_label, '\0'};
+    return add_atom_wopt(structure, atom_name, residue_name, residue_number, NULL, label, x, y, z, classifier, options);
+}
+
+int freesasa_structure_add_atom(freesasa_structure *structure, const char *atom_name, const char *residue_name,
+                                const char *residue_number, char chain_label, double x, double y, double z)
+{
+    const char label[2] = {chain_label, '\0'};
+    return add_atom_wopt(structure, atom_name, residue_name, residue_number, NULL, label, x, y, z, NULL, 0);
+}
+
+/* ---- PDB text ---------------------------------------------------------------------------------------- */
+/* the whole stream in one read (the reference measures the file with fseek/ftell too, src/util.c:20-34) */
+static struct shared_text *slurp(FILE *f)
+{
+    struct shared_text *t = calloc(1, sizeof *t);
+    long got;
+    if (!t) {
+        MEM_FAIL();
+        return NULL;
+    }
+    t->refs = 1;
+    if (fseek(f, 0, SEEK_END) != 0 || (t->len = ftell(f)) < 0) {
+        FAIL_MSG("%s", strerror(errno));
+        goto fail;
+    }
+    rewind(f);
+    if (!(t->data = malloc((size_t)t->len + 1))) {
+        MEM_FAIL();
+        goto fail;
+    }
+    got = (long)fread(t->data, 1, (size_t)t->len, f);
+    if (ferror(f)) {
+        FAIL_MSG("%s", strerror(errno));
+        goto fail;
+    }
+    t->len = got;
+    t->data[got] = '\0';
+    return t;
+fail:
+    text_release(t);
+    return NULL;
+}
+
+/* One fgets(line, 120, f) of the reference: up to 119 bytes, through the first newline.  *raw = bytes consumed,
+ * return value = strlen() of what the reference would see (an embedded NUL cuts the string). */
+static inline long next_line(const struct shared_text *t, long pos, long *raw)
+{
+    const long room = t->len - pos < LINE_MAX_STRL - 1 ? t->len - pos : LINE_MAX_STRL - 1;
+    const char *p = t->data + pos, *nl = memchr(p, '\n', (size_t)room), *nul;
+    const long n = nl ? nl - p + 1 : room;
+    *raw = n;
+    nul = memchr(p, '\0', (size_t)n);
+    return nul ? nul - p : n;
+}
+
+static inline int is_atom_line(const char *l, long len, int options)
+{
+    if (len >= 4 && memcmp(l, "ATOM", 4) == 0) return 1;
+    return (options & FREESASA_INCLUDE_HETATM) && len >= 6 && memcmp(l, "HETATM", 6) == 0;
+}
+
+/* freesasa_pdb_ishydrogen(), src/pdb.c:260-283 (the caller has established that the line is an ATOM/HETATM record,
+ * which is what pdb_line_check() re-verifies).  Non-zero = treated as hydrogen; lines shorter than 13 characters
+ * give FREESASA_FAIL there, which the caller also reads as "true". */
+static inline int is_hydrogen(const char *l, long len)
+{
+    if (len < 13) return 1;
+    if (len >= 78) { /* element symbol present, columns 77-78 */
+        if (l[76] == ' ' && (l[77] == 'H' || l[77] == 'D')) return 1;
+        if (!(l[76] == ' ' && l[77] == ' ')) return 0;
+    } else {
+        return 0; /* symbol "" is "not blank and not H or D" */
+    }
+    if (!(l[12] == ' ' || (l[12] >= '1' && l[12] <= '9'))) return 0;
+    if (l[12] == 'H' || l[13] == 'H') return 1;
+    if (l[12] == 'D' || l[13] == 'D') return 1;
+    return 0;
+}
+
+static inline int is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+/* The layout nearly every PDB file uses: three right-justified %8.3f fields.  Accepted only when reading the section
+ * as whitespace-separated tokens (what the reference does) must give the same three numbers: each field is blanks, an
+ * optional '-', 1-4 digits, '.', three digits, and fields two and three do not start with a digit (otherwise the previous
+ * token would run on).  value = integer / 1000.0, one correctly rounded division. */
+static inline int strict_coords(const char *s, double v[3])
+{
+    int k;
+    for (k = 0; k < 3; ++k, s += 8) {
+        unsigned d5 = (unsigned)(s[5] - '0'), d6 = (unsigned)(s[6] - '0'), d7 = (unsigned)(s[7] - '0'), d3 = (unsigned)(s[3] - '0');
+        int m, j, neg = 0;
+        if (s[4] != '.' || d3 > 9 || d5 > 9 || d6 > 9 || d7 > 9) return 0;
+        m = (int)d3;
+        for (j = 2; j >= 0; --j) {
+            const unsigned d = (unsigned)(s[j] - '0');
+            if (d > 9) break;
+            m += (int)d * (j == 2 ? 10 : j == 1 ? 100 : 1000);
+        }
+        if (j >= 0) {
+            if (s[j] == '-') {
+                neg = 1;
+                --j;
+            }
+            for (; j >= 0; --j)
+                if (s[j] != ' ') return 0;
+        } else if (k > 0) {
+            return 0; /* a digit in the first column of a later field: the tokens would merge */
+        }
+        m = m * 1000 + (int)(d5 * 100 + d6 * 10 + d7);
+        v[k] = neg ? -((double)m / 1000.0) : (double)m / 1000.0;
+    }
+    return 1;
+}
+
+/* Three whitespace-separated decimal numbers from the 24-character coordinate section.  Fast path: sign, at most 15
+ * digits with an optional point -> integer mantissa / 10^k, one IEEE division, which is the correctly rounded value
+ * strtod()/sscanf("%lf") return.  Anything else (exponent, hex, inf, nan, long mantissa, missing number) -> 0 and the
+ * caller repeats the reference's own sscanf. */
+static int fast_coords(const char *s, int n, double v[3])
+{
+    static const double pow10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    int i = 0, k;
+    for (k = 0; k < 3; ++k) {
+        uint64_t m = 0;
+        int neg = 0, digits = 0, frac = 0, seen_point = 0;
+        while (i < n && is_space(s[i])) ++i;
+        if (i < n && (s[i] == '-' || s[i] == '+')) neg = s[i++] == '-';
+        for (; i < n; ++i) {
+            const char c = s[i];
+            if (c >= '0' && c <= '9') {
+                m = m * 10 + (uint64_t)(c - '0');
+                ++digits;
+                frac += seen_point;
+            } else if (c == '.' && !seen_point) {
+                seen_point = 1;
+            } else {
+                break;
+            }
+        }
+        if (digits == 0 || digits > 15) return 0;
+        if (i < n && (s[i] == 'e' || s[i] == 'E' || s[i] == 'x' || s[i] == 'X' || s[i] == 'p' || s[i] == 'P')) return 0;
+        v[k] = frac ? (double)m / pow10[frac] : (double)m;
+        if (neg) v[k] = -v[k];
+    }
+    return 1;
+}
+
+/* Direct-mapped memo of classifier lookups keyed by the raw 4+3 label bytes of a line: a structure has a few hundred
+ * distinct (residue, atom) pairs, so after the first residues every lookup is one load and one compare. */
+#define MEMO_SLOTS 1024
+struct memo {
+    uint64_t key[MEMO_SLOTS];
+    int row[MEMO_SLOTS];
+};
+static inline int memo_row(struct memo *m, const freesasa_classifier *classifier, const struct atom_label *a)
+{
+    uint64_t key = 0;
+    uint32_t slot;
+    memcpy(&key, a->name, 4);
+    memcpy((char *)&key + 4, a->res_name, 3);
+    slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54);
+    if (m->key[slot] != key || key == 0) {
+        m->key[slot] = key;
+        m->row[slot] = fsb_classifier_row(classifier, a->res_name, a->name);
+    }
+    return m->row[slot];
+}
+
+/* from_pdb_impl(), src/structure.c:638-721, on the byte range [begin, end] of the text */
+static freesasa_structure *from_range(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
+                                      int options)
+{
+    freesasa_structure *s = freesasa_structure_new();
+    const freesasa_classifier *cl = classifier ? classifier : &freesasa_default_classifier;
+    struct memo *memo = calloc(1, sizeof *memo);
+    char the_alt = ' ';
+    long pos = begin, raw, len;
+
+    if (s == NULL || memo == NULL) {
+        free(memo);
+        freesasa_structure_free(s);
+        return NULL;
+    }
+    s->text = (struct shared_text *)t;
+    __atomic_add_fetch(&s->text->refs, 1, __ATOMIC_RELAXED);
+    /* an atom needs a line of at least 54 characters: size every array once, no reallocation while reading (untouched
+     * capacity costs address space only) */
+    {
+        const long span = (end < t->len ? end : t->len) - begin;
+        if (span > 0 && reserve_atoms(s, (int)(span / 54) + 1)) goto fail;
+    }
+    while (pos < t->len) {
+        const char *l = t->data + pos;
+        len = next_line(t, pos, &raw);
+        pos += raw;
+        if (pos > end) break;
+
+        if (is_atom_line(l, len, options)) {
+            struct atom_label a;
+            char alt;
+            double v[3];
+            int ret;
+
+            if (is_hydrogen(l, len) && !(options & FREESASA_INCLUDE_HYDROGEN)) continue;
+
+            /* atom_new_from_line(), src/structure.c:201-240: a field is empty when the line is too short for it */
+            alt = len > 16 ? l[16] : '\0'; /* line[16] of a 16-character line is its terminator */
+            memset(&a, 0, sizeof a);
+            if (len >= 16) memcpy(a.name, l + 12, 4);
+            if (len >= 20) memcpy(a.res_name, l + 17, 3);
+            if (len >= 27) memcpy(a.res_number, l + 22, 5);
+            a.chain[0] = len > 21 ? l[21] : '\0';
+            if (len >= 78) memcpy(a.symbol, l + 76, 2);
+            if (len < 78 || (a.symbol[0] == ' ' && a.symbol[1] == ' ')) guess_symbol(a.symbol, a.name);
+
+            /* only the first alternate location of a run is kept (src/structure.c:672-679) */
+            if ((alt != ' ' && the_alt == ' ') || alt == ' ')
+                the_alt = alt;
+            else if (alt != ' ' && alt != the_alt)
+                continue;
+
+            /* freesasa_pdb_get_coord(), src/pdb.c:176-197 */
+            if (len < 54) goto fail;
+            if (!strict_coords(l + 30, v) && !fast_coords(l + 30, 24, v)) {
+                char section[25];
+                memcpy(section, l + 30, 24);
+                section[24] = '\0';
+                if (sscanf(section, "%lf%lf%lf", &v[0], &v[1], &v[2]) != 3) {
+                    char copy[LINE_MAX_STRL];
+                    memcpy(copy, l, (size_t)len);
+                    copy[len] = '\0';
+                    FAIL_MSG("could not read coordinates from line '%s'", copy);
+                    goto fail;
+                }
+            }
+
+            ret = add_atom(s, &a, v, classifier, options, l, (size_t)len, memo_row(memo, cl, &a));
+            if (ret == FREESASA_FAIL) goto fail;
+            if (ret == FREESASA_WARN) continue;
+
+            if (options & FREESASA_RADIUS_FROM_OCCUPANCY) {
+                /* freesasa_pdb_get_occupancy() -> pdb_get_double(line + 54, 6), src/pdb.c:33-49,239-247 */
+                char buf[8];
+                float occ;
+                long w = len - 54 < 6 ? len - 54 : 6;
+                if (len < 55) goto fail;
+                memcpy(buf, l + 54, (size_t)w);
+                buf[w] = '\0';
+                if (sscanf(buf, "%f", &occ) != 1) goto fail;
+                s->radius[s->n - 1] = occ;
+            }
+        }
+
+        if (!(options & FREESASA_JOIN_MODELS)) {
+            if (len >= 5 && memcmp(l, "MODEL", 5) == 0 && len > 10) {
+                char rest[LINE_MAX_STRL];
+                memcpy(rest, l + 10, (size_t)(len - 10));
+                rest[len - 10] = '\0';
+                sscanf(rest, "%d", &s->model);
+            }
+            if (len >= 6 && memcmp(l, "ENDMDL", 6) == 0) break;
+        }
+    }
+    if (s->n == 0) {
+        FAIL_MSG("input had no valid ATOM or HETATM lines");
+        goto fail;
+    }
+    free(memo);
+    return s;
+fail:
+    FAIL_MSG("%s", "");
+    free(memo);
+    freesasa_structure_free(s);
+    return NULL;
+}
+
+freesasa_structure *freesasa_structure_from_pdb(FILE *pdb_file, const freesasa_classifier *classifier, int options)
+{
+    struct shared_text *t;
+    freesasa_structure *s;
+    assert(pdb_file);
+    if (!(t = slurp(pdb_file))) return NULL;
+    s = from_range(t, 0, t->len, classifier, options);
+    text_release(t);
+    return s;
+}
+
+/* Additive: the same reader on a memory buffer (what a caller that already holds the file bytes would use).  The
+ * bytes are copied once; the caller's buffer is not referenced after the call. */
+freesasa_structure *freesasa_structure_from_pdb_buffer(const char *text, long len, const freesasa_classifier *classifier,
+                                                       int options)
+{
+    struct shared_text *t = calloc(1, sizeof *t);
+    freesasa_structure *s;
+    assert(text);
+    if (!t || !(t->data = malloc((size_t)len + 1))) {
+        free(t);
+        MEM_FAIL();
+        return NULL;
+    }
+    memcpy(t->data, text, (size_t)len);
+    t->data[len] = '\0';
+    t->len = len;
+    t->refs = 1;
+    s = from_range(t, 0, len, classifier, options);
+    text_release(t);
+    return s;
+}
+
+/* ---- models and chains as separate structures (freesasa_structure_array(), src/structure.c:848-953) ------------ */
+struct range {
+    long begin, end;
+};
+
+/* freesasa_pdb_get_models(), src/pdb.c:51-98 */
+static int find_models(const struct shared_text *t, struct range **out)
+{
+    struct range *m = NULL;
+    int n = 0, n_end = 0, cap = 0;
+    long pos = 0, raw, len;
+    while (pos < t->len) {
+        const char *l = t->data + pos;
+        len = next_line(t, pos, &raw);
+        if (len >= 5 && memcmp(l, "MODEL", 5) == 0) {
+            if (n == cap) {
+                void *p = realloc(m, sizeof(struct range) * (size_t)(cap = 2 * cap + 8));
+                if (!p) {
+                    free(m);
+                    *out = NULL;
+                    return MEM_FAIL();
+                }
+                m = p;
+            }
+            m[n].begin = pos;
+            m[n].end = 0;
+            ++n;
+        }
+        if (len >= 6 && memcmp(l, "ENDMDL", 6) == 0) {
+            ++n_end;
+            if (n != n_end) {
+                free(m);
+                *out = NULL;
+                return FAIL_MSG("mismatch between MODEL and ENDMDL in input");
+            }
+            m[n - 1].end = pos + raw;
+        }
+        pos += raw;
+    }
+    if (n == 0) {
+        free(m);
+        m = NULL;
+    }
+    *out = m;
+    return n;
+}
+
+/* freesasa_pdb_get_chains(), src/pdb.c:100-150: a new range starts whenever the chain column of an atom line differs
+ * from the previous atom line's; only lines that end strictly before model.end are looked at */
+static int find_chains(const struct shared_text *t, struct range model, struct range **out, int options)
+{
+    struct range *c = NULL;
+    int n = 0, cap = 0;
+    char last_chain = '\0';
+    long pos = model.begin, last_pos = model.begin, raw, len;
+    *out = NULL;
+    while (pos < t->len) {
+        const char *l = t->data + pos;
+        len = next_line(t, pos, &raw);
+        if (!(pos + raw < model.end)) break;
+        if (is_atom_line(l, len, options)) {
+            const char chain = len > 21 ? l[21] : '\0';
+            if (chain != last_chain) {
+                if (n > 0) c[n - 1].end = last_pos;
+                if (n == cap) {
+                    void *p = realloc(c, sizeof(struct range) * (size_t)(cap = 2 * cap + 8));
+                    if (!p) {
+                        free(c);
+                        return MEM_FAIL();
+                    }
+                    c = p;
+                }
+                c[n++].begin = last_pos;
+                last_chain = chain;
+            }
+        }
+        pos += raw;
+        last_pos = pos;
+    }
+    if (n > 0) {
+        c[n - 1].end = last_pos;
+        c[0].begin = model.begin; /* keeps the MODEL record */
+        *out = c;
+    }
+    return n;
+}
+
+freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_classifier *classifier, int options)
+{
+    struct shared_text *t;
+    struct range *models = NULL, *chains = NULL, whole;
+    freesasa_structure **ss = NULL;
+    int n_models, n_total = 0, i, j;
+
+    assert(pdb);
+    assert(n);
+    *n = 0;
+    if (!((options & FREESASA_SEPARATE_MODELS) || (options & FREESASA_SEPARATE_CHAINS))) {
+        FAIL_MSG("options need to specify at least one of FREESASA_SEPARATE_CHAINS and FREESASA_SEPARATE_MODELS");
+        return NULL;
+    }
+    if (!(t = slurp(pdb))) return NULL;
+    whole.begin = 0;
+    whole.end = t->len;
+    n_models = find_models(t, &models);
+    if (n_models == FREESASA_FAIL) {
+        FAIL_MSG("problems reading PDB-file");
+        text_release(t);
+        return NULL;
+    }
+    if (n_models == 0) {
+        models = &whole;
+        n_models = 1;
+    }
+    if (!(options & FREESASA_SEPARATE_MODELS)) n_models = 1; /* only the first model */
+
+    if (options & FREESASA_SEPARATE_CHAINS) {
+        for (i = 0; i < n_models; ++i) {
+            void *p;
+            const int n_new = find_chains(t, models[i], &chains, options);
+            if (n_new == FREESASA_FAIL) goto fail;
+            if (n_new == 0) {
+                WARN_MSG("in %s(): no chains found (in model %d)", __func__, i + 1);
+                continue;
+            }
+            if (!(p = realloc(ss, sizeof(freesasa_structure *) * (size_t)(n_total + n_new)))) {
+                MEM_FAIL();
+                goto fail;
+            }
+            ss = p;
+            for (j = 0; j < n_new; ++j) ss[n_total + j] = NULL;
+            n_total += n_new;
+            for (j = 0; j < n_new; ++j) {
+                ss[n_total - n_new + j] = from_range(t, chains[j].begin, chains[j].end, classifier, options);
+                if (ss[n_total - n_new + j] == NULL) goto fail;
+                ss[n_total - n_new + j]->model = i + 1;
+            }
+            free(chains);
+            chains = NULL;
+        }
+    } else {
+        if (!(ss = calloc((size_t)n_models, sizeof(freesasa_structure *)))) {
+            MEM_FAIL();
+            goto fail;
+        }
+        n_total = n_models;
+        for (i = 0; i < n_models; ++i) {
+            ss[i] = from_range(t, models[i].begin, models[i].end, classifier, options);
+            if (ss[i] == NULL) goto fail;
+            ss[i]->model = i + 1;
+        }
+    }
+    if (n_total == 0) goto fail;
+    if (models != &whole) free(models);
+    text_release(t);
+    *n = n_total;
+    return ss;
+fail:
+    if (ss)
+        for (i = 0; i < n_total; ++i) freesasa_structure_free(ss[i]);
+    if (models != &whole) free(models);
+    free(chains);
+    free(ss);
+    text_release(t);
+    *n = 0;
+    return NULL;
+}
+
+/* freesasa_structure_get_chains(), src/structure.c:955-1010 */
+freesasa_structure *freesasa_structure_get_chains(const freesasa_structure *structure, const char *chains,
+                                                  const freesasa_classifier *classifier, int options)
+{
+    freesasa_structure *out;
+    int i;
+    assert(structure);
+    if (strlen(chains) == 0) return NULL;
+    if (!(out = freesasa_structure_new())) return NULL;
+    out->model = structure->model;
+    for (i = 0; i < structure->n; ++i) {
+        const struct atom_label *a = &structure->label[i];
+        if (strchr(chains, a->chain[0]) != NULL) {
+            const double *v = structure->coord.xyz + 3 * i;
+            if (add_atom_wopt(out, a->name, a->res_name, a->res_number, a->symbol, a->chain, v[0], v[1], v[2], classifier,
+                              options) == FREESASA_FAIL) {
+                FAIL_MSG("%s", "");
+                goto fail;
+            }
+        }
+    }
+    if (out->n == 0) goto fail;
+    if ((size_t)out->n_chains != strlen(chains)) {
+        FAIL_MSG("structure has chains '%s', but '%s' requested", structure->short_labels, chains);
+        goto fail;
+    }
+    return out;
+fail:
+    freesasa_structure_free(out);
+    return NULL;
+}
+
+/* ---- accessors (src/structure.c:1083-1424) ------------------------------------------------------------ */
+#define ATOM_OK(s, i) (assert(s), assert((i) >= 0 && (i) < (s)->n))
+#define RES_OK(s, r) (assert(s), assert((r) >= 0 && (r) < (s)->n_res))
+
+const char *freesasa_structure_chain_labels(const freesasa_structure *s) { return s->short_labels; }
+int freesasa_structure_n(const freesasa_structure *s) { return s->n; }
+int freesasa_structure_n_residues(const freesasa_structure *s) { return s->n_res; }
+int freesasa_structure_n_chains(const freesasa_structure *s) { return s->n_chains; }
+const double *freesasa_structure_radius(const freesasa_structure *s) { return s->radius; }
+void freesasa_structure_set_radius(freesasa_structure *s, const double *radii)
+{
+    assert(s);
+    assert(radii);
+    memcpy(s->radius, radii, (size_t)s->n * sizeof(double));
+}
+const char *freesasa_structure_atom_name(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].name; }
+const char *freesasa_structure_atom_res_name(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].res_name; }
+const char *freesasa_structure_atom_res_number(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].res_number; }
+char freesasa_structure_atom_chain(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].chain[0]; }
+const char *freesasa_structure_atom_chain_lcl(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].chain; }
+const char *freesasa_structure_atom_symbol(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].symbol; }
+double freesasa_structure_atom_radius(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->radius[i]; }
+void freesasa_structure_atom_set_radius(freesasa_structure *s, int i, double radius) { ATOM_OK(s, i); s->radius[i] = radius; }
+freesasa_atom_class freesasa_structure_atom_class(const freesasa_structure *s, int i) { ATOM_OK(s, i); return (freesasa_atom_class)s->cls[i]; }
+/* src/structure.c:1199-1206: the line as fgets() delivered it (with its newline), NULL for atoms added by hand.
+ * The NUL-terminated copies are built for the whole structure on the first call. */
+const char *freesasa_structure_atom_pdb_line(const freesasa_structure *s, int i)
+{
+    ATOM_OK(s, i);
+    if (s->line_at[i] < 0) return NULL;
+    if (__atomic_load_n(&s->lines, __ATOMIC_ACQUIRE) == NULL) {
+        static pthread_mutex_t once = PTHREAD_MUTEX_INITIALIZER;
+        pthread_mutex_lock(&once);
+        if (s->lines == NULL) {
+            char *all = malloc((size_t)s->n * LINE_MAX_STRL);
+            int k;
+            if (all == NULL) {
+                pthread_mutex_unlock(&once);
+                MEM_FAIL();
+                return NULL;
+            }
+            for (k = 0; k < s->n; ++k) {
+                if (s->line_at[k] >= 0) memcpy(all + (size_t)k * LINE_MAX_STRL, s->text->data + s->line_at[k], s->line_len[k]);
+                all[(size_t)k * LINE_MAX_STRL + (s->line_at[k] >= 0 ? s->line_len[k] : 0)] = '\0';
+            }
+            __atomic_store_n((char **)&s->lines, all, __ATOMIC_RELEASE);
+        }
+        pthread_mutex_unlock(&once);
+    }
+    return s->lines + (size_t)i * LINE_MAX_STRL;
+}
+int fsb_structure_atom_residue(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->res_index[i]; }
+
+const char *freesasa_structure_residue_name(const freesasa_structure *s, int r) { RES_OK(s, r); return s->label[s->res_first[r]].res_name; }
+const char *freesasa_structure_residue_number(const freesasa_structure *s, int r) { RES_OK(s, r); return s->label[s->res_first[r]].res_number; }
+char freesasa_structure_residue_chain(const freesasa_structure *s, int r) { RES_OK(s, r); return s->label[s->res_first[r]].chain[0]; }
+const freesasa_nodearea *freesasa_structure_residue_reference(const freesasa_structure *s, int r)
+{
+    RES_OK(s, r);
+    return s->res_has_ref[r] ? &s->res_ref[r] : NULL;
+}
+int freesasa_structure_residue_atoms(const freesasa_structure *s, int r, int *first, int *last)
+{
+    RES_OK(s, r);
+    assert(first);
+    assert(last);
+    *first = s->res_first[r];
+    *last = r == s->n_res - 1 ? s->n - 1 : s->res_first[r + 1] - 1;
+    return FREESASA_SUCCESS;
+}
+
+static int chain_index(const freesasa_structure *s, const char *chain)
+{
+    int i;
+    for (i = 0; i < s->n_chains; ++i)
+        if (strncmp(s->chain_label[i], chain, 4) == 0) return i;
+    return FAIL_MSG("chain '%s' not found", chain);
+}
+/* src/structure.c:1303-1325: a chain's atoms run up to the first atom of the next registered chain */
+int freesasa_structure_chain_atoms(const freesasa_structure *s, char chain, int *first, int *last)
+{
+    const char label[2] = {chain, '\0'};
+    int c;
+    assert(s);
+    if ((c = chain_index(s, label)) < 0) return FAIL_MSG("%s", "");
+    *first = s->chain_first[c];
+    *last = c == s->n_chains - 1 ? s->n - 1 : s->chain_first[c + 1] - 1;
+    return FREESASA_SUCCESS;
+}
+int freesasa_structure_chain_residues(const freesasa_structure *s, char chain, int *first, int *last)
+{
+    int fa, la;
+    assert(s);
+    if (freesasa_structure_chain_atoms(s, chain, &fa, &la)) return FAIL_MSG("%s", "");
+    *first = s->res_index[fa];
+    *last = s->res_index[la];
+    return FREESASA_SUCCESS;
+}
+const char *freesasa_structure_chain_label(const freesasa_structure *s, int index)
+{
+    assert(s);
+    assert(index >= 0 && index < s->n_chains);
+    return s->chain_label[index];
+}
+int freesasa_structure_model(const freesasa_structure *s) { return s->model; }
+void freesasa_structure_set_model(freesasa_structure *s, int model) { s->model = model; }
+const char *freesasa_structure_classifier_name(const freesasa_structure *s) { return s->classifier_name; }
+const double *freesasa_structure_coord_array(const freesasa_structure *s) { return s->coord.xyz; }
+const coord_t *freesasa_structure_xyz(const freesasa_structure *s) { return &s->coord; }
+
+/* ---- into the engine ------------------------------------------------------------------------------------ */
+/* src/freesasa.c:144-153 */
+freesasa_result *freesasa_calc_structure(const freesasa_structure *structure, const freesasa_parameters *parameters)
+{
+    assert(structure);
+    return freesasa_calc(freesasa_structure_xyz(structure), freesasa_structure_radius(structure), parameters);
+}
+
+/* Row f-2: what the CLI's loop over structures (src/main.cc:334-362: one freesasa_calc_tree per model / chain group)
+ * becomes with a batched engine: every structure of the array in one device pass. */
+int freesasa_calc_structure_batch(int n_struct, freesasa_structure *const *structures, const freesasa_parameters *parameters,
+                                  freesasa_result **results)
+{
+    const double **xyz, **radii;
+    int *n_atoms, k, rc;
+    if (n_struct <= 0 || !structures || !results) return FAIL_MSG("invalid batch arguments");
+    xyz = malloc(sizeof(double *) * (size_t)n_struct);
+    radii = malloc(sizeof(double *) * (size_t)n_struct);
+    n_atoms = malloc(sizeof(int) * (size_t)n_struct);
+    if (!xyz || !radii || !n_atoms) {
+        rc = MEM_FAIL();
+    } else {
+        for (k = 0; k < n_struct; ++k) {
+            assert(structures[k]);
+            xyz[k] = structures[k]->coord.xyz;
+            radii[k] = structures[k]->radius;
+            n_atoms[k] = structures[k]->n;
+        }
+        rc = freesasa_calc_coord_batch(n_struct, xyz, radii, n_atoms, parameters, results);
+    }
+    free(xyz);
+    free(radii);
+    free(n_atoms);
+    return rc;
+}

@@ -70,6 +70,100 @@ typedef struct freesasa_parameters freesasa_parameters;
 typedef struct freesasa_result freesasa_result;
 #endif
 
+/* ---- row f-1 of the scope table: classifiers and structure ingest ---------------------------------- */
+/* reference src/freesasa.h:163-167 */
+enum freesasa_atom_class { FREESASA_ATOM_APOLAR = 0, FREESASA_ATOM_POLAR = 1, FREESASA_ATOM_UNKNOWN = 2 };
+/* reference src/freesasa.h:182-191 */
+enum freesasa_structure_options {
+    FREESASA_INCLUDE_HETATM = 1,
+    FREESASA_INCLUDE_HYDROGEN = 1 << 2,
+    FREESASA_SEPARATE_MODELS = 1 << 3,
+    FREESASA_SEPARATE_CHAINS = 1 << 4,
+    FREESASA_JOIN_MODELS = 1 << 5,
+    FREESASA_HALT_AT_UNKNOWN = 1 << 6,
+    FREESASA_SKIP_UNKNOWN = 1 << 7,
+    FREESASA_RADIUS_FROM_OCCUPANCY = 1 << 8
+};
+/* reference src/freesasa.h:289-297 */
+struct freesasa_nodearea {
+    const char *name;
+    double total, main_chain, side_chain, polar, apolar, unknown;
+};
+#define FREESASA_CONFLICTING_CLASSIFIERS "conflicting-classifiers" /* src/freesasa.h:133 */
+
+typedef struct freesasa_classifier freesasa_classifier; /* opaque, src/freesasa.h:345 */
+typedef struct freesasa_structure freesasa_structure;   /* opaque, src/freesasa.h:353 */
+#ifndef __cplusplus
+typedef enum freesasa_atom_class freesasa_atom_class;
+typedef struct freesasa_nodearea freesasa_nodearea;
+#endif
+
+/* built-in classifiers, reference src/freesasa.h:418-436 (tables generated from the compiled reference) */
+extern const freesasa_classifier freesasa_protor_classifier;
+extern const freesasa_classifier freesasa_naccess_classifier;
+extern const freesasa_classifier freesasa_oons_classifier;
+#define freesasa_default_classifier freesasa_protor_classifier /* src/freesasa.h:124 */
+
+/* reference src/freesasa.h:545-607, src/classifier.c:781-866 */
+freesasa_classifier *freesasa_classifier_from_file(FILE *file);
+void freesasa_classifier_free(freesasa_classifier *classifier);
+double freesasa_classifier_radius(const freesasa_classifier *classifier, const char *res_name, const char *atom_name);
+freesasa_atom_class freesasa_classifier_class(const freesasa_classifier *classifier, const char *res_name,
+                                              const char *atom_name);
+const char *freesasa_classifier_class2str(freesasa_atom_class atom_class);
+const char *freesasa_classifier_name(const freesasa_classifier *classifier);
+/* internal to the reference (src/classifier.h:72-78, src/freesasa_internal.h), exported for the parity tests */
+double freesasa_guess_radius(const char *symbol);
+const freesasa_nodearea *freesasa_classifier_residue_reference(const freesasa_classifier *classifier, const char *res_name);
+int freesasa_atom_is_backbone(const char *atom_name);
+
+/* reference src/freesasa.h:749-1446, src/structure.c */
+freesasa_structure *freesasa_structure_new(void);
+void freesasa_structure_free(freesasa_structure *structure);
+freesasa_structure *freesasa_structure_from_pdb(FILE *pdb, const freesasa_classifier *classifier, int options);
+freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_classifier *classifier, int options);
+int freesasa_structure_add_atom(freesasa_structure *structure, const char *atom_name, const char *residue_name,
+                                const char *residue_number, char chain_label, double x, double y, double z);
+int freesasa_structure_add_atom_wopt(freesasa_structure *structure, const char *atom_name, const char *residue_name,
+                                     const char *residue_number, char chain_label, double x, double y, double z,
+                                     const freesasa_classifier *classifier, int options);
+freesasa_structure *freesasa_structure_get_chains(const freesasa_structure *structure, const char *chains,
+                                                  const freesasa_classifier *classifier, int options);
+const char *freesasa_structure_chain_labels(const freesasa_structure *structure);
+int freesasa_structure_n(const freesasa_structure *structure);
+int freesasa_structure_n_residues(const freesasa_structure *structure);
+int freesasa_structure_n_chains(const freesasa_structure *structure);
+const double *freesasa_structure_radius(const freesasa_structure *structure);
+void freesasa_structure_set_radius(freesasa_structure *structure, const double *radii);
+const char *freesasa_structure_atom_name(const freesasa_structure *structure, int i);
+const char *freesasa_structure_atom_res_name(const freesasa_structure *structure, int i);
+const char *freesasa_structure_atom_res_number(const freesasa_structure *structure, int i);
+char freesasa_structure_atom_chain(const freesasa_structure *structure, int i);
+const char *freesasa_structure_atom_chain_lcl(const freesasa_structure *structure, int i);
+const char *freesasa_structure_atom_symbol(const freesasa_structure *structure, int i);
+double freesasa_structure_atom_radius(const freesasa_structure *structure, int i);
+void freesasa_structure_atom_set_radius(freesasa_structure *structure, int i, double radius);
+freesasa_atom_class freesasa_structure_atom_class(const freesasa_structure *structure, int i);
+const char *freesasa_structure_atom_pdb_line(const freesasa_structure *structure, int i);
+const char *freesasa_structure_residue_name(const freesasa_structure *structure, int r_i);
+const char *freesasa_structure_residue_number(const freesasa_structure *structure, int r_i);
+char freesasa_structure_residue_chain(const freesasa_structure *structure, int r_i);
+const freesasa_nodearea *freesasa_structure_residue_reference(const freesasa_structure *structure, int r_i);
+int freesasa_structure_residue_atoms(const freesasa_structure *structure, int r_i, int *first, int *last);
+int freesasa_structure_chain_atoms(const freesasa_structure *structure, char chain, int *first, int *last);
+int freesasa_structure_chain_residues(const freesasa_structure *structure, char chain, int *first, int *last);
+const char *freesasa_structure_chain_label(const freesasa_structure *structure, int index);
+int freesasa_structure_model(const freesasa_structure *structure);
+void freesasa_structure_set_model(freesasa_structure *structure, int model);
+const char *freesasa_structure_classifier_name(const freesasa_structure *structure);
+const double *freesasa_structure_coord_array(const freesasa_structure *structure);
+const coord_t *freesasa_structure_xyz(const freesasa_structure *structure);
+freesasa_result *freesasa_calc_structure(const freesasa_structure *structure, const freesasa_parameters *parameters);
+/* Additive (row f-2): all structures of an array (NMR models, separated chains; the serial loop of
+ * src/main.cc:334-362) in ONE device pass.  results[k] as in freesasa_calc_coord_batch(). */
+int freesasa_calc_structure_batch(int n_struct, freesasa_structure *const *structures,
+                                  const freesasa_parameters *parameters, freesasa_result **results);
+
 extern const freesasa_parameters freesasa_default_parameters;
 extern const int FREESASA_DEF_NUMBER_THREADS;
 

@@ -121,6 +121,6 @@ def test_product_never_touches_oracle():
     pkg = os.path.join(ROOT, "freesasa_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".inc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU", ""), os.path.join(dirpath, f)
