@@ -1,0 +1,528 @@
+/* freesasa_b200/csrc/areas.c — per-atom SASA -> areas of residues, chains, structures (the result tree).
+ *
+ * Scope row f-3 of SURVEY.md §8(f).  Mirrors the reference's node API (src/freesasa.h:1449-1850, src/node.c) and its
+ * class sums (freesasa_result_classes(), src/classifier.c:829-838): same node types, same parent/children/next
+ * topology, same names and properties, and the same areas TO THE BIT — every sum is formed in the reference's order
+ * (atoms of a residue in sequence, residues of a chain in sequence, chains of a structure in sequence; src/node.c:148-
+ * 176,718-777), which is what makes a sum of doubles reproducible.
+ *
+ * What differs is the construction.  The reference builds the tree with one malloc per node, one per area and four to
+ * five strdup per atom (name, chain, residue number, residue name, PDB line; src/node.c:214-277) and frees it node by
+ * node.  Here one result (freesasa_tree_add_result) is ONE allocation: a header, the node array (result, structure,
+ * chains, residues, atoms — in that order, children contiguous), the area array and a string pool in which the atoms of
+ * a residue share the residue's strings.  PDB lines are not copied: the block keeps a reference on the text the
+ * structure was read from and materialises NUL-terminated lines the first time one is asked for.  Building the tree for
+ * 100k atoms is a single pass of ~25 ns/atom; freeing it is one free().
+ *
+ * The segmented sums stay on the host on purpose: with host-resident results (the drop-in contract returns `sasa[]` in
+ * malloc'd host memory) a device epilogue would have to upload 5 B/atom of keys to save ~1 ns/atom of
+ * additions.
+ */
+#include "host_internal.h"
+
+#include <assert.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct tree_block;
+
+struct freesasa_node {
+    const char *name;
+    freesasa_nodetype type;
+    freesasa_nodearea *area;
+    freesasa_node *parent, *children, *next;
+    union {
+        struct {
+            int is_polar, is_bb, index; /* index: atom number inside its block */
+            double radius;
+            const char *chain, *res_number, *res_name;
+        } atom;
+        struct {
+            int n_atoms;
+            const char *number;
+            const freesasa_nodearea *reference;
+        } residue;
+        struct {
+            int n_residues;
+        } chain;
+        struct {
+            int n_chains, n_atoms, model;
+            const char *chain_labels;
+            freesasa_result *result;
+        } structure;
+        struct {
+            const char *classified_by;
+            freesasa_parameters parameters;
+            int n_structures;
+            struct tree_block *block;
+        } result;
+    } p;
+};
+
+/* one freesasa_tree_add_result(): everything below lives in the same allocation as this header */
+struct tree_block {
+    int n_atoms;
+    struct shared_text *text; /* referenced, may be NULL */
+    long *line_at;
+    unsigned char *line_len;
+    char *volatile lines; /* separately allocated on demand */
+    freesasa_result result;
+};
+
+const freesasa_nodearea freesasa_nodearea_null = {NULL, 0, 0, 0, 0, 0, 0};
+
+/* ---- area arithmetic (src/node.c:718-777) --------------------------------------------------------------------- */
+static inline void atom_area(freesasa_nodearea *area, double a, int is_bb, int cls)
+{
+    *area = freesasa_nodearea_null;
+    area->total = a;
+    if (is_bb)
+        area->main_chain = a;
+    else
+        area->side_chain = a;
+    switch (cls) {
+    case FREESASA_ATOM_APOLAR: area->apolar = a; break;
+    case FREESASA_ATOM_POLAR: area->polar = a; break;
+    case FREESASA_ATOM_UNKNOWN: area->unknown = a; break;
+    }
+}
+
+int freesasa_atom_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
+                           int atom_index)
+{
+    atom_area(area, result->sasa[atom_index], freesasa_atom_is_backbone(structure->label[atom_index].name),
+              structure->cls[atom_index]);
+    return FREESASA_SUCCESS;
+}
+
+void freesasa_add_nodearea(freesasa_nodearea *sum, const freesasa_nodearea *term)
+{
+    sum->total += term->total;
+    sum->side_chain += term->side_chain;
+    sum->main_chain += term->main_chain;
+    sum->polar += term->polar;
+    sum->apolar += term->apolar;
+    sum->unknown += term->unknown;
+}
+
+void freesasa_range_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
+                             int first_atom, int last_atom)
+{
+    freesasa_nodearea term;
+    int i;
+    assert(area);
+    assert(structure);
+    assert(result);
+    assert(first_atom <= last_atom);
+    for (i = first_atom; i <= last_atom; ++i) {
+        freesasa_atom_nodearea(&term, structure, result, i);
+        freesasa_add_nodearea(area, &term);
+    }
+}
+
+/* src/classifier.c:829-838 */
+freesasa_nodearea freesasa_result_classes(const freesasa_structure *structure, const freesasa_result *result)
+{
+    freesasa_nodearea area = {"whole-structure", 0, 0, 0, 0, 0, 0};
+    freesasa_range_nodearea(&area, structure, result, 0, freesasa_structure_n(structure) - 1);
+    return area;
+}
+
+/* ---- construction ------------------------------------------------------------------------------------------- */
+static size_t align8(size_t n) { return (n + 7) & ~(size_t)7; }
+
+freesasa_node *freesasa_tree_new(void)
+{
+    freesasa_node *root = calloc(1, sizeof *root);
+    if (root == NULL) {
+        MEM_FAIL();
+        return NULL;
+    }
+    root->type = FREESASA_NODE_ROOT;
+    return root;
+}
+
+static void block_free(freesasa_node *result_node)
+{
+    struct tree_block *b = result_node->p.result.block;
+    fsb_text_release(b->text);
+    free(b->lines);
+    free(b); /* nodes, areas, strings and the cloned result all live in this allocation */
+}
+
+/* freesasa_tree_add_result(), src/node.c:441-476, with node_structure/node_chain/node_residue/node_atom
+ * (src/node.c:214-409) fused into one pass */
+int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *s, const char *name)
+{
+    const int n = s->n, n_res = s->n_res, n_chains = s->n_chains;
+    const size_t n_nodes = 2 + (size_t)n_chains + (size_t)n_res + (size_t)n;
+    const size_t name_len = name ? strlen(name) + 1 : 0, cls_len = strlen(s->classifier_name ? s->classifier_name : "") + 1;
+    const size_t labels_len = strlen(s->short_labels ? s->short_labels : "") + 1;
+    /* string pool: result name, classifier name, chain labels (twice: structure name and property), per chain 4,
+     * per residue name 4 + number 6 (+ 4 for a chain label of its own, rarely used), per atom name 5 (+ 4 for a residue
+     * name that differs from its residue node's; untouched capacity otherwise) */
+    const size_t pool = name_len + cls_len + 2 * labels_len + 4 * (size_t)n_chains + 14 * (size_t)n_res + 9 * (size_t)n;
+    size_t off_nodes, off_areas, off_refs, off_sasa, off_lines, off_len, off_pool, total;
+    char *mem, *str;
+    struct tree_block *b;
+    freesasa_node *nodes, *rnode, *snode, *chain_nodes, *res_nodes, *atom_nodes;
+    freesasa_nodearea *areas, *refs;
+    int c, r, i, n_ref = 0;
+
+    assert(tree);
+    assert(tree->type == FREESASA_NODE_ROOT);
+    if (s->classifier_name == NULL || n == 0) return FAIL_MSG("structure without atoms");
+
+    for (r = 0; r < n_res; ++r) n_ref += s->res_has_ref[r] != 0;
+    off_nodes = align8(sizeof(struct tree_block));
+    off_areas = off_nodes + n_nodes * sizeof(freesasa_node);
+    off_refs = off_areas + n_nodes * sizeof(freesasa_nodearea);
+    off_sasa = off_refs + (size_t)n_ref * sizeof(freesasa_nodearea);
+    off_lines = off_sasa + (size_t)n * sizeof(double);
+    off_len = off_lines + (size_t)n * sizeof(long);
+    off_pool = align8(off_len + (size_t)n);
+    total = off_pool + pool;
+    if (!(mem = malloc(total))) {
+        MEM_FAIL();
+        return FAIL_MSG("%s", "");
+    }
+    b = (struct tree_block *)mem;
+    nodes = (freesasa_node *)(mem + off_nodes);
+    areas = (freesasa_nodearea *)(mem + off_areas);
+    refs = (freesasa_nodearea *)(mem + off_refs);
+    str = mem + off_pool;
+
+    b->n_atoms = n;
+    b->text = s->text;
+    if (b->text) __atomic_add_fetch(&b->text->refs, 1, __ATOMIC_RELAXED);
+    b->line_at = (long *)(mem + off_lines);
+    b->line_len = (unsigned char *)(mem + off_len);
+    b->lines = NULL;
+    memcpy(b->line_at, s->line_at, (size_t)n * sizeof(long));
+    memcpy(b->line_len, s->line_len, (size_t)n);
+    /* freesasa_result_clone(), src/freesasa.c:184-205 */
+    b->result = *result;
+    b->result.sasa = (double *)(mem + off_sasa);
+    memcpy(b->result.sasa, result->sasa, (size_t)n * sizeof(double));
+
+    rnode = nodes;
+    snode = nodes + 1;
+    chain_nodes = nodes + 2;
+    res_nodes = chain_nodes + n_chains;
+    atom_nodes = res_nodes + n_res;
+
+#define POOL(dst, src, len)            \
+    do {                               \
+        memcpy(str, (src), (len));     \
+        (dst) = str;                   \
+        str += (len);                  \
+    } while (0)
+
+    /* result node: no area, no parent (src/node.c:148-156,441-470) */
+    memset(rnode, 0, sizeof *rnode);
+    rnode->type = FREESASA_NODE_RESULT;
+    if (name) POOL(rnode->name, name, name_len);
+    POOL(rnode->p.result.classified_by, s->classifier_name, cls_len);
+    rnode->p.result.parameters = result->parameters;
+    rnode->p.result.n_structures = 1;
+    rnode->p.result.block = b;
+    rnode->children = snode;
+
+    memset(snode, 0, sizeof *snode);
+    snode->type = FREESASA_NODE_STRUCTURE;
+    POOL(snode->name, s->short_labels, labels_len);
+    POOL(snode->p.structure.chain_labels, s->short_labels, labels_len);
+    snode->p.structure.n_chains = n_chains;
+    snode->p.structure.n_atoms = n;
+    snode->p.structure.model = s->model;
+    snode->p.structure.result = &b->result;
+    snode->parent = rnode;
+    snode->children = chain_nodes;
+    snode->area = &areas[1];
+
+    /* atoms: one pass; residues and chains pick their ranges up afterwards */
+    for (i = 0; i < n; ++i) {
+        freesasa_node *a = &atom_nodes[i];
+        const struct atom_label *l = &s->label[i];
+        freesasa_node *res = &res_nodes[s->res_index[i]];
+        a->type = FREESASA_NODE_ATOM;
+        POOL(a->name, l->name, 5);
+        a->area = &areas[2 + n_chains + n_res + i];
+        a->parent = res;
+        a->children = NULL;
+        a->next = a + 1; /* the last atom of each residue is cut below */
+        a->p.atom.is_polar = s->cls[i] == FREESASA_ATOM_POLAR;
+        a->p.atom.is_bb = freesasa_atom_is_backbone(l->name);
+        a->p.atom.index = i;
+        a->p.atom.radius = s->radius[i];
+        atom_area(a->area, result->sasa[i], a->p.atom.is_bb, s->cls[i]); /* name stays NULL, as in src/node.c:269-270 */
+    }
+    /* chains: names and residue ranges first (the residues need their parent), sums afterwards */
+    for (c = 0; c < n_chains; ++c) {
+        freesasa_node *ch = &chain_nodes[c];
+        const int first_atom = s->chain_first[c], last_atom = c == n_chains - 1 ? n - 1 : s->chain_first[c + 1] - 1;
+        const int first_res = s->res_index[first_atom], last_res = s->res_index[last_atom];
+        ch->type = FREESASA_NODE_CHAIN;
+        POOL(ch->name, s->chain_label[c], 4);
+        ch->p.chain.n_residues = last_res - first_res + 1;
+        ch->parent = snode;
+        ch->children = &res_nodes[first_res];
+        ch->next = c == n_chains - 1 ? NULL : ch + 1;
+        ch->area = &areas[2 + c];
+        for (r = first_res; r <= last_res; ++r) {
+            res_nodes[r].parent = ch;
+            res_nodes[r].next = r == last_res ? NULL : &res_nodes[r + 1];
+        }
+    }
+    for (r = 0; r < n_res; ++r) {
+        freesasa_node *res = &res_nodes[r];
+        const int first = s->res_first[r], last = r == n_res - 1 ? n - 1 : s->res_first[r + 1] - 1;
+        const struct atom_label *l = &s->label[first];
+        const char *number, *chain = res->parent->name;
+        freesasa_nodearea *sum = &areas[2 + n_chains + r];
+        res->type = FREESASA_NODE_RESIDUE;
+        POOL(res->name, l->res_name, 4);
+        POOL(number, l->res_number, 6);
+        /* an atom reports its own chain label; it differs from the chain node it hangs under only when a chain label
+         * comes back after another one (A, B, A: the second run of A is filed under B, src/structure.c:1303-1325) */
+        if (memcmp(l->chain, chain, 4) != 0) POOL(chain, l->chain, 4);
+        res->p.residue.number = number;
+        res->p.residue.n_atoms = last - first + 1;
+        res->p.residue.reference = NULL;
+        if (s->res_has_ref[r]) { /* a copy: the tree may outlive the structure (src/node.c:303-315) */
+            *refs = s->res_ref[r];
+            res->p.residue.reference = refs++;
+        }
+        res->children = &atom_nodes[first];
+        res->area = sum;
+        *sum = freesasa_nodearea_null;
+        sum->name = res->name;
+        for (i = first; i <= last; ++i) {
+            freesasa_node *a = &atom_nodes[i];
+            freesasa_add_nodearea(sum, a->area);
+            a->p.atom.res_name = res->name; /* residues are delimited by number and chain only: names may differ inside */
+            if (memcmp(s->label[i].res_name, l->res_name, 4) != 0) POOL(a->p.atom.res_name, s->label[i].res_name, 4);
+            a->p.atom.res_number = number;
+            a->p.atom.chain = chain;
+        }
+        atom_nodes[last].next = NULL;
+    }
+    for (c = 0; c < n_chains; ++c) {
+        freesasa_node *ch = &chain_nodes[c], *res;
+        *ch->area = freesasa_nodearea_null;
+        ch->area->name = ch->name;
+        for (res = ch->children; res; res = res->next) freesasa_add_nodearea(ch->area, res->area);
+    }
+    *snode->area = freesasa_nodearea_null;
+    snode->area->name = snode->name;
+    for (c = 0; c < n_chains; ++c) freesasa_add_nodearea(snode->area, chain_nodes[c].area);
+#undef POOL
+    assert((size_t)(str - (mem + off_pool)) <= pool);
+
+    /* prepend to the root's list (src/node.c:467-468) */
+    rnode->next = tree->children;
+    tree->children = rnode;
+    return FREESASA_SUCCESS;
+}
+
+freesasa_node *freesasa_tree_init(const freesasa_result *result, const freesasa_structure *structure, const char *name)
+{
+    freesasa_node *tree = freesasa_tree_new();
+    if (tree == NULL) {
+        FAIL_MSG("%s", "");
+    } else if (freesasa_tree_add_result(tree, result, structure, name) == FREESASA_FAIL) {
+        FAIL_MSG("%s", "");
+        freesasa_node_free(tree);
+        tree = NULL;
+    }
+    return tree;
+}
+
+/* src/node.c:478-503 */
+int freesasa_tree_join(freesasa_node *tree1, freesasa_node **tree2)
+{
+    freesasa_node *child;
+    assert(tree1);
+    assert(tree2);
+    assert(*tree2);
+    assert(tree1->type == FREESASA_NODE_ROOT);
+    assert((*tree2)->type == FREESASA_NODE_ROOT);
+    child = tree1->children;
+    if (child != NULL) {
+        while (child->next) child = child->next;
+        child->next = (*tree2)->children;
+    } else {
+        tree1->children = (*tree2)->children;
+    }
+    free(*tree2);
+    *tree2 = NULL;
+    return FREESASA_SUCCESS;
+}
+
+/* src/node.c:505-513.  Result nodes have no parent in the reference either (src/node.c:441-470), so a result taken
+ * out of context can be freed on its own there; here as well. */
+int freesasa_node_free(freesasa_node *root)
+{
+    freesasa_node *r, *next;
+    if (root == NULL) return FREESASA_SUCCESS;
+    if (root->parent || (root->type != FREESASA_NODE_ROOT && root->type != FREESASA_NODE_RESULT))
+        return FAIL_MSG("can't free node that isn't the root of its tree");
+    if (root->type == FREESASA_NODE_RESULT) {
+        block_free(root);
+        return FREESASA_SUCCESS;
+    }
+    for (r = root->children; r; r = next) {
+        next = r->next;
+        block_free(r);
+    }
+    free(root);
+    return FREESASA_SUCCESS;
+}
+
+/* src/freesasa.c:155-182 */
+freesasa_node *freesasa_calc_tree(const freesasa_structure *structure, const freesasa_parameters *parameters, const char *name)
+{
+    freesasa_node *tree = NULL;
+    freesasa_result *result;
+    assert(structure);
+    result = freesasa_calc(freesasa_structure_xyz(structure), freesasa_structure_radius(structure), parameters);
+    if (result != NULL)
+        tree = freesasa_tree_init(result, structure, name);
+    else
+        FAIL_MSG("%s", "");
+    if (tree == NULL) FAIL_MSG("%s", "");
+    freesasa_result_free(result);
+    return tree;
+}
+
+/* ---- accessors (src/node.c:515-716) ----------------------------------------------------------------------- */
+const freesasa_nodearea *freesasa_node_area(const freesasa_node *node)
+{
+    assert(node->type != FREESASA_NODE_ROOT);
+    return node->area;
+}
+freesasa_node *freesasa_node_children(freesasa_node *node) { return node->children; }
+freesasa_node *freesasa_node_next(freesasa_node *node) { return node->next; }
+freesasa_node *freesasa_node_parent(freesasa_node *node) { return node->parent; }
+freesasa_nodetype freesasa_node_type(const freesasa_node *node) { return node->type; }
+const char *freesasa_node_name(const freesasa_node *node) { return node->name; }
+const char *freesasa_node_classified_by(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_RESULT);
+    return node->p.result.classified_by;
+}
+int freesasa_node_atom_is_polar(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_ATOM);
+    return node->p.atom.is_polar;
+}
+int freesasa_node_atom_is_mainchain(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_ATOM);
+    return node->p.atom.is_bb;
+}
+double freesasa_node_atom_radius(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_ATOM);
+    return node->p.atom.radius;
+}
+const char *freesasa_node_atom_residue_number(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_ATOM);
+    return node->p.atom.res_number;
+}
+const char *freesasa_node_atom_residue_name(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_ATOM);
+    return node->p.atom.res_name;
+}
+const char *freesasa_node_atom_chain(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_ATOM);
+    return node->p.atom.chain;
+}
+/* the PDB record the atom was read from (with its newline), NULL for atoms added by hand; copies are made for the
+ * whole block the first time any line is requested */
+const char *freesasa_node_atom_pdb_line(const freesasa_node *node)
+{
+    static pthread_mutex_t once = PTHREAD_MUTEX_INITIALIZER;
+    const freesasa_node *r;
+    struct tree_block *b;
+    int i;
+    assert(node->type == FREESASA_NODE_ATOM);
+    r = node->parent->parent->parent->parent; /* residue, chain, structure, result */
+    b = r->p.result.block;
+    i = node->p.atom.index;
+    if (b->line_at[i] < 0) return NULL;
+    if (__atomic_load_n(&b->lines, __ATOMIC_ACQUIRE) == NULL) {
+        pthread_mutex_lock(&once);
+        if (b->lines == NULL) {
+            char *all = malloc((size_t)b->n_atoms * LINE_MAX_STRL);
+            int k;
+            if (all == NULL) {
+                pthread_mutex_unlock(&once);
+                MEM_FAIL();
+                return NULL;
+            }
+            for (k = 0; k < b->n_atoms; ++k) {
+                const int len = b->line_at[k] >= 0 ? b->line_len[k] : 0;
+                if (len) memcpy(all + (size_t)k * LINE_MAX_STRL, b->text->data + b->line_at[k], (size_t)len);
+                all[(size_t)k * LINE_MAX_STRL + len] = '\0';
+            }
+            __atomic_store_n((char **)&b->lines, all, __ATOMIC_RELEASE);
+        }
+        pthread_mutex_unlock(&once);
+    }
+    return b->lines + (size_t)i * LINE_MAX_STRL;
+}
+int freesasa_node_residue_n_atoms(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_RESIDUE);
+    return node->p.residue.n_atoms;
+}
+const char *freesasa_node_residue_number(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_RESIDUE);
+    return node->p.residue.number;
+}
+const freesasa_nodearea *freesasa_node_residue_reference(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_RESIDUE);
+    return node->p.residue.reference;
+}
+int freesasa_node_chain_n_residues(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_CHAIN);
+    return node->p.chain.n_residues;
+}
+int freesasa_node_structure_n_chains(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    return node->p.structure.n_chains;
+}
+int freesasa_node_structure_n_atoms(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    return node->p.structure.n_atoms;
+}
+int freesasa_node_structure_model(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    return node->p.structure.model;
+}
+const char *freesasa_node_structure_chain_labels(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    return node->p.structure.chain_labels;
+}
+const freesasa_result *freesasa_node_structure_result(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    return node->p.structure.result;
+}
+const freesasa_parameters *freesasa_node_result_parameters(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_RESULT);
+    return &node->p.result.parameters;
+}

@@ -28,4 +28,54 @@ static inline int fsb_token(const char *s, const char **begin)
     return (int)(q - p);
 }
 
+/* ---- structure storage (ingest.c), shared with the result tree (areas.c) --------------------------------------- */
+#define LINE_MAX_STRL 120 /* PDB_MAX_LINE_STRL, src/pdb.h:22: fgets() buffer of the reference, longer lines are split */
+
+/* the bytes a set of structures was read from, shared by reference count (freesasa_structure_array() makes several
+ * structures from one file) */
+struct shared_text {
+    char *data;
+    long len;
+    int refs;
+};
+void fsb_text_release(struct shared_text *t); /* drops one reference */
+
+/* fixed-width, NUL-terminated label fields of one atom (widths: src/pdb.h:17-20, src/structure.c:30-32) */
+struct atom_label {
+    char name[5];
+    char res_name[4];
+    char res_number[6];
+    char symbol[3];
+    char chain[4];
+};
+
+struct freesasa_structure {
+    int n, cap;
+    coord_t coord; /* coord.xyz owned, 3*cap doubles; what freesasa_calc() receives */
+    double *radius;
+    struct atom_label *label;
+    int *res_index;
+    unsigned char *cls;
+    /* PDB lines are not copied while reading: the structure keeps a reference to the text it was read from and a
+     * slice per atom; NUL-terminated copies are made only if somebody asks for them (atom_pdb_line) */
+    struct shared_text *text;
+    long *line_at;           /* offset into text->data, -1 = the atom did not come from a PDB line */
+    unsigned char *line_len; /* <= 119 */
+    char *volatile lines;    /* lazily built: n strings of stride LINE_MAX_STRL */
+    /* residues */
+    int n_res, cap_res;
+    int *res_first;
+    freesasa_nodearea *res_ref;
+    unsigned char *res_has_ref;
+    /* chains, in order of first appearance */
+    int n_chains, cap_chains;
+    char (*chain_label)[4];
+    char *short_labels;
+    int *chain_first;
+    char *classifier_name;
+    const freesasa_classifier *last_classifier; /* classifier of the previous add: skips re-registering its name */
+    int model;
+};
+
+
 #endif

@@ -33,63 +33,18 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define LINE_MAX_STRL 120 /* PDB_MAX_LINE_STRL, src/pdb.h:22: fgets() buffer of the reference, longer lines are split */
 
 int fsb_classifier_row(const freesasa_classifier *c, const char *res_name, const char *atom_name);
 double fsb_classifier_row_radius(const freesasa_classifier *c, int row);
 int fsb_classifier_row_class(const freesasa_classifier *c, int row);
 
-/* the bytes a set of structures was read from, shared by reference count (freesasa_structure_array() makes several
- * structures from one file) */
-struct shared_text {
-    char *data;
-    long len;
-    int refs;
-};
-static void text_release(struct shared_text *t)
+void fsb_text_release(struct shared_text *t)
 {
     if (t && __atomic_sub_fetch(&t->refs, 1, __ATOMIC_ACQ_REL) == 0) {
         free(t->data);
         free(t);
     }
 }
-
-/* fixed-width, NUL-terminated label fields of one atom (widths: src/pdb.h:17-20, src/structure.c:30-32) */
-struct atom_label {
-    char name[5];
-    char res_name[4];
-    char res_number[6];
-    char symbol[3];
-    char chain[4];
-};
-
-struct freesasa_structure {
-    int n, cap;
-    coord_t coord; /* coord.xyz owned, 3*cap doubles; what freesasa_calc() receives */
-    double *radius;
-    struct atom_label *label;
-    int *res_index;
-    unsigned char *cls;
-    /* PDB lines are not copied while reading: the structure keeps a reference to the text it was read from and a
-     * slice per atom; NUL-terminated copies are made only if somebody asks for them (atom_pdb_line) */
-    struct shared_text *text;
-    long *line_at;           /* offset into text->data, -1 = the atom did not come from a PDB line */
-    unsigned char *line_len; /* <= 119 */
-    char *volatile lines;    /* lazily built: n strings of stride LINE_MAX_STRL */
-    /* residues */
-    int n_res, cap_res;
-    int *res_first;
-    freesasa_nodearea *res_ref;
-    unsigned char *res_has_ref;
-    /* chains, in order of first appearance */
-    int n_chains, cap_chains;
-    char (*chain_label)[4];
-    char *short_labels;
-    int *chain_first;
-    char *classifier_name;
-    const freesasa_classifier *last_classifier; /* classifier of the previous add: skips re-registering its name */
-    int model;
-};
 
 /* ---- storage ---------------------------------------------------------------------------------------- */
 static int reserve_atoms(freesasa_structure *s, int cap)
@@ -134,7 +89,7 @@ void freesasa_structure_free(freesasa_structure *s)
     free(s->line_at);
     free(s->line_len);
     free(s->lines);
-    text_release(s->text);
+    fsb_text_release(s->text);
     free(s->res_first);
     free(s->res_ref);
     free(s->res_has_ref);
@@ -364,7 +319,7 @@ static struct shared_text *slurp(FILE *f)
     t->data[got] = '\0';
     return t;
 fail:
-    text_release(t);
+    fsb_text_release(t);
     return NULL;
 }
 
@@ -608,7 +563,7 @@ freesasa_structure *freesasa_structure_from_pdb(FILE *pdb_file, const freesasa_c
     assert(pdb_file);
     if (!(t = slurp(pdb_file))) return NULL;
     s = from_range(t, 0, t->len, classifier, options);
-    text_release(t);
+    fsb_text_release(t);
     return s;
 }
 
@@ -630,7 +585,7 @@ freesasa_structure *freesasa_structure_from_pdb_buffer(const char *text, long le
     t->len = len;
     t->refs = 1;
     s = from_range(t, 0, len, classifier, options);
-    text_release(t);
+    fsb_text_release(t);
     return s;
 }
 
@@ -741,7 +696,7 @@ freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_
     n_models = find_models(t, &models);
     if (n_models == FREESASA_FAIL) {
         FAIL_MSG("problems reading PDB-file");
-        text_release(t);
+        fsb_text_release(t);
         return NULL;
     }
     if (n_models == 0) {
@@ -788,7 +743,7 @@ freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_
     }
     if (n_total == 0) goto fail;
     if (models != &whole) free(models);
-    text_release(t);
+    fsb_text_release(t);
     *n = n_total;
     return ss;
 fail:
@@ -797,7 +752,7 @@ fail:
     if (models != &whole) free(models);
     free(chains);
     free(ss);
-    text_release(t);
+    fsb_text_release(t);
     *n = 0;
     return NULL;
 }

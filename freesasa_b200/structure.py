@@ -262,3 +262,105 @@ def api() -> StructureAPI:
 
         _api = StructureAPI(_host_lib(), _CResult, Parameters)
     return _api
+
+
+# ------------------------------------------------------------------------------------------------------------
+# result tree (scope row f-3): ctypes view of the node API, reference src/freesasa.h:1449-1850
+# ------------------------------------------------------------------------------------------------------------
+NODE_ATOM, NODE_RESIDUE, NODE_CHAIN, NODE_STRUCTURE, NODE_RESULT, NODE_ROOT = range(6)
+
+
+class TreeAPI:
+    """The reference's tree entry points bound on ``api.lib``; ``walk`` flattens a tree for comparisons."""
+
+    def __init__(self, api: StructureAPI):
+        self.api, L = api, api.lib
+        cp, ci, cd = ctypes.c_char_p, ctypes.c_int, ctypes.c_double
+        res_p, par_p = ctypes.POINTER(api.Result), ctypes.POINTER(api.Parameters)
+
+        def sig(name, restype, *argtypes):
+            f = getattr(L, name)
+            f.restype, f.argtypes = restype, list(argtypes)
+
+        sig("freesasa_tree_new", _vp)
+        sig("freesasa_tree_init", _vp, res_p, _vp, cp)
+        sig("freesasa_tree_add_result", ci, _vp, res_p, _vp, cp)
+        sig("freesasa_tree_join", ci, _vp, ctypes.POINTER(_vp))
+        sig("freesasa_calc_tree", _vp, _vp, par_p, cp)
+        sig("freesasa_node_free", ci, _vp)
+        sig("freesasa_result_classes", NodeArea, _vp, res_p)
+        sig("freesasa_node_area", ctypes.POINTER(NodeArea), _vp)
+        for name in ("children", "next", "parent"):
+            sig("freesasa_node_" + name, _vp, _vp)
+        sig("freesasa_node_type", ci, _vp)
+        for name in ("name", "classified_by", "atom_pdb_line", "atom_residue_number", "atom_residue_name", "atom_chain",
+                     "residue_number", "structure_chain_labels"):
+            sig("freesasa_node_" + name, cp, _vp)
+        for name in ("atom_is_polar", "atom_is_mainchain", "residue_n_atoms", "chain_n_residues", "structure_n_chains",
+                     "structure_n_atoms", "structure_model"):
+            sig("freesasa_node_" + name, ci, _vp)
+        sig("freesasa_node_atom_radius", cd, _vp)
+        sig("freesasa_node_residue_reference", ctypes.POINTER(NodeArea), _vp)
+        sig("freesasa_node_structure_result", res_p, _vp)
+        sig("freesasa_node_result_parameters", par_p, _vp)
+
+    def make_result(self, sasa: np.ndarray, parameters=None):
+        """A caller-owned freesasa_result over ``sasa`` (kept alive by the returned tuple)."""
+        sasa = np.ascontiguousarray(sasa, dtype=np.float64)
+        r = self.api.Result()
+        r.total = float(np.add.reduce(sasa)) if False else float(sum(sasa.tolist()))  # serial sum, src/freesasa.c:113-116
+        r.sasa = sasa.ctypes.data_as(_dp)
+        r.n_atoms = int(sasa.shape[0])
+        r.parameters = parameters if parameters is not None else self.api.Parameters(0, 1.4, 100, 20, 1)
+        return r, sasa
+
+    def init(self, result, structure: Structure, name: bytes):
+        return self.api.lib.freesasa_tree_init(ctypes.byref(result), structure.h, name)
+
+    def free(self, root):
+        return self.api.lib.freesasa_node_free(root)
+
+    def classes(self, structure: Structure, result):
+        a = self.api.lib.freesasa_result_classes(structure.h, ctypes.byref(result))
+        return (a.name,) + tuple(np.float64(v).view(np.uint64).item() for v in a.values())
+
+    def walk(self, node, depth=0, out=None):
+        """Pre-order list of (depth, type, name, area bits, properties) for the subtree under ``node``."""
+        L = self.api.lib
+        out = [] if out is None else out
+        bits = lambda v: np.float64(v).view(np.uint64).item()  # noqa: E731
+        t = L.freesasa_node_type(node)
+        area = None
+        if t not in (NODE_ROOT, NODE_RESULT):
+            a = L.freesasa_node_area(node).contents
+            area = (a.name,) + tuple(bits(v) for v in a.values())
+        if t == NODE_ATOM:
+            props = (L.freesasa_node_atom_is_polar(node), L.freesasa_node_atom_is_mainchain(node),
+                     bits(L.freesasa_node_atom_radius(node)), L.freesasa_node_atom_pdb_line(node),
+                     L.freesasa_node_atom_residue_number(node), L.freesasa_node_atom_residue_name(node),
+                     L.freesasa_node_atom_chain(node))
+        elif t == NODE_RESIDUE:
+            ref = L.freesasa_node_residue_reference(node)
+            props = (L.freesasa_node_residue_n_atoms(node), L.freesasa_node_residue_number(node),
+                     (ref.contents.name, ref.contents.values()) if ref else None)
+        elif t == NODE_CHAIN:
+            props = (L.freesasa_node_chain_n_residues(node),)
+        elif t == NODE_STRUCTURE:
+            res = L.freesasa_node_structure_result(node).contents
+            n = res.n_atoms
+            props = (L.freesasa_node_structure_n_chains(node), L.freesasa_node_structure_n_atoms(node),
+                     L.freesasa_node_structure_model(node), L.freesasa_node_structure_chain_labels(node), bits(res.total), n,
+                     np.ctypeslib.as_array(res.sasa, shape=(n,)).view(np.uint64).tolist())
+        elif t == NODE_RESULT:
+            p = L.freesasa_node_result_parameters(node).contents
+            props = (L.freesasa_node_classified_by(node), p.alg, p.probe_radius, p.shrake_rupley_n_points,
+                     p.lee_richards_n_slices, p.n_threads)
+        else:
+            props = ()
+        parent = L.freesasa_node_parent(node)
+        out.append((depth, t, L.freesasa_node_name(node), area, props, bool(parent)))
+        child = L.freesasa_node_children(node)
+        while child:
+            self.walk(child, depth + 1, out)
+            child = L.freesasa_node_next(child)
+        return out

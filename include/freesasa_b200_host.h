@@ -164,6 +164,64 @@ freesasa_result *freesasa_calc_structure(const freesasa_structure *structure, co
 int freesasa_calc_structure_batch(int n_struct, freesasa_structure *const *structures,
                                   const freesasa_parameters *parameters, freesasa_result **results);
 
+/* ---- row f-3: areas of residues, chains and structures (the result tree) ------------------------------ */
+/* reference src/freesasa.h:307-315 */
+enum freesasa_nodetype {
+    FREESASA_NODE_ATOM,
+    FREESASA_NODE_RESIDUE,
+    FREESASA_NODE_CHAIN,
+    FREESASA_NODE_STRUCTURE,
+    FREESASA_NODE_RESULT,
+    FREESASA_NODE_ROOT,
+    FREESASA_NODE_NONE
+};
+typedef struct freesasa_node freesasa_node; /* opaque, src/freesasa.h:361 */
+#ifndef __cplusplus
+typedef enum freesasa_nodetype freesasa_nodetype;
+#endif
+extern const freesasa_nodearea freesasa_nodearea_null; /* src/freesasa_internal.h, src/node.c:64 */
+
+/* reference src/freesasa.h:497-519,1460-1549 */
+freesasa_node *freesasa_calc_tree(const freesasa_structure *structure, const freesasa_parameters *parameters, const char *name);
+freesasa_nodearea freesasa_result_classes(const freesasa_structure *structure, const freesasa_result *result);
+freesasa_node *freesasa_tree_new(void);
+freesasa_node *freesasa_tree_init(const freesasa_result *result, const freesasa_structure *structure, const char *name);
+int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *structure,
+                             const char *name);
+int freesasa_tree_join(freesasa_node *tree1, freesasa_node **tree2);
+int freesasa_node_free(freesasa_node *root);
+/* reference src/freesasa.h:1559-1850 */
+const freesasa_nodearea *freesasa_node_area(const freesasa_node *node);
+freesasa_node *freesasa_node_children(freesasa_node *node);
+freesasa_node *freesasa_node_next(freesasa_node *node);
+freesasa_node *freesasa_node_parent(freesasa_node *node);
+freesasa_nodetype freesasa_node_type(const freesasa_node *node);
+const char *freesasa_node_name(const freesasa_node *node);
+const char *freesasa_node_classified_by(const freesasa_node *node);
+int freesasa_node_atom_is_polar(const freesasa_node *node);
+int freesasa_node_atom_is_mainchain(const freesasa_node *node);
+double freesasa_node_atom_radius(const freesasa_node *node);
+const char *freesasa_node_atom_pdb_line(const freesasa_node *node);
+const char *freesasa_node_atom_residue_number(const freesasa_node *node);
+const char *freesasa_node_atom_residue_name(const freesasa_node *node);
+const char *freesasa_node_atom_chain(const freesasa_node *node);
+int freesasa_node_residue_n_atoms(const freesasa_node *node);
+const char *freesasa_node_residue_number(const freesasa_node *node);
+const freesasa_nodearea *freesasa_node_residue_reference(const freesasa_node *node);
+int freesasa_node_chain_n_residues(const freesasa_node *node);
+int freesasa_node_structure_n_chains(const freesasa_node *node);
+int freesasa_node_structure_n_atoms(const freesasa_node *node);
+int freesasa_node_structure_model(const freesasa_node *node);
+const char *freesasa_node_structure_chain_labels(const freesasa_node *node);
+const freesasa_result *freesasa_node_structure_result(const freesasa_node *node);
+const freesasa_parameters *freesasa_node_result_parameters(const freesasa_node *node);
+/* reference src/freesasa_internal.h (used by the tree and the writers) */
+int freesasa_atom_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
+                           int atom_index);
+void freesasa_add_nodearea(freesasa_nodearea *sum, const freesasa_nodearea *term);
+void freesasa_range_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
+                             int first_atom, int last_atom);
+
 extern const freesasa_parameters freesasa_default_parameters;
 extern const int FREESASA_DEF_NUMBER_THREADS;
 

@@ -1,0 +1,145 @@
+"""CPU tests for scope row f-3: per-atom SASA -> areas of residues, chains, structures and classes.
+
+The sums are floating point, but the order of every addition is the reference's (src/node.c:148-176,718-777), so the
+bar is bit-exact: the whole tree — topology, names, properties, every component of every area — is compared with the
+tree the compiled reference builds from the same structure and the same per-atom values.  No GPU is involved: the
+per-atom values are seeded random numbers or the CPU restatement's SASA.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from freesasa_b200 import structure as st
+from freesasa_b200 import workloads as w
+from oracle import bindings as ob
+
+needs_ref = pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def both():
+    mine = st.api()
+    ref = st.StructureAPI(ob.ref_lib(), ob.RefResult, ob.RefParameters)
+    for api in (mine, ref):
+        api.lib.freesasa_set_verbosity(2)
+    return (mine, st.TreeAPI(mine)), (ref, st.TreeAPI(ref))
+
+
+CASES = [
+    dict(n_atoms=300, seed=1),
+    dict(n_atoms=800, seed=2, chains=4, hydrogens=0.2, hetatm=3, unknown=0.1),
+    dict(n_atoms=500, seed=3, chains=2, altloc=0.1),
+    dict(n_atoms=2500, seed=4, chains=7),
+]
+
+
+def trees_for(both, text, options, sasa_seed, name=b"test"):
+    out = []
+    for api, tree in both:
+        s = api.from_pdb(text, None, options)
+        rng = np.random.default_rng(sasa_seed)
+        sasa = rng.uniform(0, 60, size=s.n) * (rng.random(s.n) < 0.6)  # many exact zeros, like buried atoms
+        result, keep = tree.make_result(sasa)
+        root = tree.init(result, s, name)
+        assert root
+        out.append((tree.walk(root), tree.classes(s, result)))
+        assert tree.free(root) == 0
+        del keep
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("options", [0, st.INCLUDE_HETATM | st.INCLUDE_HYDROGEN])
+def test_tree_is_bit_identical(both, case, options):
+    text = w.pdb_text(**CASES[case]).encode()
+    (mine_walk, mine_classes), (ref_walk, ref_classes) = trees_for(both, text, options, 100 + case)
+    assert len(mine_walk) == len(ref_walk)
+    for a, b in zip(mine_walk, ref_walk):
+        assert a == b
+    assert mine_classes == ref_classes
+
+
+@needs_ref
+def test_tree_with_oracle_sasa_and_odd_chains(both):
+    """Chains that come back (A, B, A), blank chains, insertion codes; per-atom values from the CPU restatement."""
+    from tests.test_ingest import EDGE_TEXTS
+
+    for tag in ("chain_returns", "blank_chain", "insertion_codes", "same_number_new_chain", "altloc_runs", "nucleic"):
+        text = EDGE_TEXTS[tag].encode()
+        walks = []
+        for api, tree in both:
+            s = api.from_pdb(text)
+            sasa = ob.oracle_calc(s.xyz(), s.radii(), ob.LEE_RICHARDS, 1.4, 20)
+            result, keep = tree.make_result(sasa)
+            root = tree.init(result, s, tag.encode())
+            walks.append(tree.walk(root))
+            tree.free(root)
+        assert walks[0] == walks[1], tag
+
+
+@needs_ref
+def test_add_result_and_join(both):
+    text1 = w.pdb_text(200, seed=11, chains=2).encode()
+    text2 = w.pdb_text(150, seed=12).encode()
+    walks = []
+    for api, tree in both:
+        L = api.lib
+        s1, s2 = api.from_pdb(text1), api.from_pdb(text2)
+        r1, k1 = tree.make_result(np.linspace(0, 30, s1.n))
+        r2, k2 = tree.make_result(np.linspace(5, 50, s2.n))
+        root = L.freesasa_tree_new()
+        assert L.freesasa_tree_add_result(root, ctypes.byref(r1), s1.h, b"first") == 0
+        assert L.freesasa_tree_add_result(root, ctypes.byref(r2), s2.h, b"second") == 0  # prepended (src/node.c:467)
+        other = ctypes.c_void_p(tree.init(r2, s2, None))
+        assert L.freesasa_tree_join(root, ctypes.byref(other)) == 0 and not other.value
+        s1.free()
+        s2.free()  # the tree owns copies of everything it needs
+        walks.append(tree.walk(root))
+        assert L.freesasa_node_free(L.freesasa_node_children(L.freesasa_node_children(root))) == -1  # not a root
+        tree.free(root)
+    assert walks[0] == walks[1]
+    assert [x[2] for x in walks[0] if x[1] == st.NODE_RESULT] == [b"second", b"first", None]
+
+
+def test_known_sums():
+    """Hand-checkable: two residues, areas 1..5, class and backbone split (src/node.c:718-746)."""
+    mine = st.api()
+    tree = st.TreeAPI(mine)
+    s = mine.new()
+    for k, (name, res, num) in enumerate([(b" N  ", b"ALA", b"   1 "), (b" CA ", b"ALA", b"   1 "), (b" CB ", b"ALA", b"   1 "),
+                                          (b" O  ", b"GLY", b"   2 "), (b" XX ", b"GLY", b"   2 ")]):
+        s.add_atom(name, res, num, b"A", 4.0 * k, 0.0, 0.0)
+    result, keep = tree.make_result(np.array([1.0, 2.0, 3.0, 4.0, 5.0]))
+    root = tree.init(result, s, b"x")
+    walk = tree.walk(root)
+    f = lambda bits: np.uint64(bits).view(np.float64).item()  # noqa: E731
+    areas = {(t, name): tuple(f(v) for v in area[1:]) for _, t, name, area, _, _ in walk if area}
+    #                                     total main side polar apolar unknown
+    assert areas[(st.NODE_RESIDUE, b"ALA")] == (6.0, 3.0, 3.0, 1.0, 5.0, 0.0)
+    assert areas[(st.NODE_RESIDUE, b"GLY")] == (9.0, 4.0, 5.0, 4.0, 0.0, 5.0)
+    assert areas[(st.NODE_CHAIN, b"A")] == (15.0, 7.0, 8.0, 5.0, 5.0, 5.0)
+    assert areas[(st.NODE_STRUCTURE, b"A")] == (15.0, 7.0, 8.0, 5.0, 5.0, 5.0)
+    assert tree.classes(s, result)[0] == b"whole-structure"
+    tree.free(root)
+
+
+REAL = ["1ubq", "1d3z", "2jo4", "3bzd_trimmed", "2isk", "1sui"]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", REAL)
+def test_reference_test_files(both, name):
+    """The reference's own test structures (dev container only): whole tree, with and without hetero atoms/hydrogens."""
+    import os
+
+    path = f"/root/reference/tests/data/{name}.pdb"
+    if not os.path.exists(path):
+        pytest.skip("reference test data not present")
+    with open(path, "rb") as f:
+        text = f.read()
+    for options in (0, st.INCLUDE_HETATM | st.INCLUDE_HYDROGEN | st.JOIN_MODELS):
+        (mine_walk, mine_classes), (ref_walk, ref_classes) = trees_for(both, text, options, 7, name.encode())
+        assert mine_walk == ref_walk
+        assert mine_classes == ref_classes
