@@ -1,0 +1,80 @@
+"""File-to-areas pipeline on the GPU box: PDB text -> structure (row f-1) -> SASA (hot path) -> result tree (row f-3),
+this repo's host layer + B200 engine beside the compiled reference on the box's host cores, stage by stage, on the same
+bytes.  Writes gpurun_out/pipeline.json.
+
+    python tests/tools/measure_pipeline.py [--quick]
+"""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import freesasa_b200 as fs  # noqa: E402
+from freesasa_b200 import structure as st  # noqa: E402
+from freesasa_b200 import workloads as w  # noqa: E402
+from oracle import bindings as ob  # noqa: E402
+
+
+def timed(fn, reps):
+    best, out = 1e30, None
+    for _ in range(reps):
+        t = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t)
+    return best * 1e3, out
+
+
+def stages(api, text, params, reps, free_between=True):
+    """ms for read / calc / tree / free; the tree's structure area as a checksum."""
+    tree = st.TreeAPI(api)
+    L = api.lib
+    res_p = ctypes.POINTER(api.Result)
+    L.freesasa_calc_structure.restype = res_p
+    t_read, s = timed(lambda: api.from_pdb(text), reps)
+    t_calc, res = timed(lambda: L.freesasa_calc_structure(s.h, ctypes.byref(params)), reps)
+    t_tree, root = timed(lambda: L.freesasa_tree_init(res, s.h, b"pipeline"), reps)
+    total = next(x for x in tree.walk(L.freesasa_node_children(root), 1) if x[1] == st.NODE_STRUCTURE)[3][1] if s.n <= 20000 else None
+    t_free, _ = timed(lambda: None, 1)
+    t0 = time.perf_counter()
+    L.freesasa_node_free(root)
+    t_free = (time.perf_counter() - t0) * 1e3
+    sasa = np.ctypeslib.as_array(res.contents.sasa, shape=(s.n,)).copy()
+    return {"atoms": s.n, "read_ms": t_read, "calc_ms": t_calc, "tree_ms": t_tree, "tree_free_ms": t_free,
+            "total_ms": t_read + t_calc + t_tree}, sasa, total
+
+
+def main():
+    quick = "--quick" in sys.argv
+    threads = min(16, os.cpu_count() or 1)
+    mine = st.api()
+    ref = st.StructureAPI(ob.ref_lib(), ob.RefResult, ob.RefParameters)
+    for api in (mine, ref):
+        api.lib.freesasa_set_verbosity(1)
+    out = {"host_threads_reference": threads, "cases": {}}
+    for name, n_atoms, chains in [("14k (2isk-sized)", 13928, 4), ("100k", 100000, 8)] + ([] if quick else [("1M", 1000000, 60)]):
+        text = w.pdb_text(n_atoms, seed=5, chains=chains).encode()
+        case = {"bytes": len(text)}
+        for alg, res_n, key in [(fs.LEE_RICHARDS, 100, "LR-100"), (fs.LEE_RICHARDS, 20, "LR-20")]:
+            reps = 3 if n_atoms <= 100000 else 1
+            m, sasa_m, _ = stages(mine, text, fs.Parameters(alg, 1.4, res_n, res_n, 1), reps + 2)
+            entry = {"this_repo": m}
+            if n_atoms <= 100000 or key == "LR-20":
+                r, sasa_r, _ = stages(ref, text, ob.RefParameters(alg, 1.4, res_n, res_n, threads), 1 if n_atoms > 20000 else reps)
+                entry["reference"] = r
+                entry["max_abs_err"] = float(np.abs(sasa_m - sasa_r).max())
+                entry["speedup_total"] = r["total_ms"] / m["total_ms"]
+            case[key] = entry
+            print(name, key, json.dumps(entry), flush=True)
+        out["cases"][name] = case
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "pipeline.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
