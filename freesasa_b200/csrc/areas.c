@@ -526,3 +526,60 @@ const freesasa_parameters *freesasa_node_result_parameters(const freesasa_node *
     assert(node->type == FREESASA_NODE_RESULT);
     return &node->p.result.parameters;
 }
+
+/* ---- per-atom writer (scope row f-4): PDB with radius and SASA in the occupancy / B-factor columns ------------------ */
+const char *freesasa_string = "freesasa-b200 (FreeSASA 2.1.3 API)";
+
+/* write_pdb_impl(), src/pdb.c:284-345: the first 54 columns of the original record, then "%6.2f%6.2f" of radius and
+ * area (which ends the line: the reference's sprintf terminates the buffer there), a TER record numbered one past the
+ * last atom's serial, ENDMDL */
+static int write_structure_pdb(FILE *output, freesasa_node *structure)
+{
+    char buf[81], serial[6];
+    freesasa_node *chain, *residue, *atom;
+    const char *last_res_name = NULL, *last_res_number = NULL, *last_chain = NULL;
+    const int model = freesasa_node_structure_model(structure);
+
+    if (model > 0)
+        fprintf(output, "MODEL     %4d\n", model);
+    else
+        fprintf(output, "MODEL        1\n");
+    memset(buf, 0, sizeof buf);
+    for (chain = structure->children; chain; chain = chain->next) {
+        for (residue = chain->children; residue; residue = residue->next) {
+            for (atom = residue->children; atom; atom = atom->next) {
+                const char *line = freesasa_node_atom_pdb_line(atom);
+                if (line == NULL) return FAIL_MSG("PDB input not valid or not present");
+                strncpy(buf, line, 80);
+                sprintf(&buf[54], "%6.2f%6.2f", atom->p.atom.radius, atom->area->total);
+                fprintf(output, "%s\n", buf);
+            }
+            last_res_name = residue->name;
+            last_res_number = residue->p.residue.number;
+        }
+        last_chain = chain->name;
+    }
+    memcpy(serial, &buf[6], 5);
+    serial[5] = '\0';
+    fprintf(output, "TER   %5d     %4s %c%5s\nENDMDL\n", atoi(serial) + 1, last_res_name, last_chain[0], last_res_number);
+    fflush(output);
+    if (ferror(output)) return FAIL_MSG("write error");
+    return FREESASA_SUCCESS;
+}
+
+/* src/pdb.c:347-375 */
+int freesasa_write_pdb(FILE *output, freesasa_node *root)
+{
+    freesasa_node *result, *structure;
+    assert(output);
+    assert(root);
+    assert(root->type == FREESASA_NODE_ROOT);
+    fprintf(output, "REMARK 999 This PDB file was generated by %s.\n", freesasa_string);
+    fprintf(output, "REMARK 999 In the ATOM records temperature factors have been\n"
+                    "REMARK 999 replaced by the SASA of the atom, and the occupancy\n"
+                    "REMARK 999 by the radius used in the calculation.\n");
+    for (result = root->children; result; result = result->next)
+        for (structure = result->children; structure; structure = structure->next)
+            if (write_structure_pdb(output, structure) == FREESASA_FAIL) return FAIL_MSG("%s", "");
+    return FREESASA_SUCCESS;
+}

@@ -308,7 +308,7 @@ class TreeAPI:
         """A caller-owned freesasa_result over ``sasa`` (kept alive by the returned tuple)."""
         sasa = np.ascontiguousarray(sasa, dtype=np.float64)
         r = self.api.Result()
-        r.total = float(np.add.reduce(sasa)) if False else float(sum(sasa.tolist()))  # serial sum, src/freesasa.c:113-116
+        r.total = float(np.cumsum(sasa)[-1]) if sasa.size else 0.0  # serial sum in atom order, src/freesasa.c:113-116
         r.sasa = sasa.ctypes.data_as(_dp)
         r.n_atoms = int(sasa.shape[0])
         r.parameters = parameters if parameters is not None else self.api.Parameters(0, 1.4, 100, 20, 1)

@@ -215,6 +215,10 @@ int freesasa_node_structure_model(const freesasa_node *node);
 const char *freesasa_node_structure_chain_labels(const freesasa_node *node);
 const freesasa_result *freesasa_node_structure_result(const freesasa_node *node);
 const freesasa_parameters *freesasa_node_result_parameters(const freesasa_node *node);
+/* row f-4, per-atom writer: reference src/freesasa_internal.h:200, src/pdb.c:347-375 (what the CLI's --format=pdb and
+ * freesasa_tree_export(..., FREESASA_PDB) emit) */
+int freesasa_write_pdb(FILE *output, freesasa_node *root);
+extern const char *freesasa_string;
 /* reference src/freesasa_internal.h (used by the tree and the writers) */
 int freesasa_atom_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
                            int atom_index);

@@ -66,6 +66,7 @@ def test_parameter_validation_like_reference(built, capfd):
     """reference src/sasa_lr.c:177-183, src/sasa_sr.c:188-193 and tests/test-cli.in:162-164,194-196:
     more than 16 threads and non-positive resolutions are errors (NULL result) before any compute."""
     H = fs._host_lib()
+    H.freesasa_set_verbosity(0)  # FREESASA_V_NORMAL, whatever earlier tests left behind
     xyz = np.zeros(3)
     rad = np.ones(1)
     dp = ctypes.POINTER(ctypes.c_double)

@@ -23,7 +23,8 @@ def both():
     ref = st.StructureAPI(ob.ref_lib(), ob.RefResult, ob.RefParameters)
     for api in (mine, ref):
         api.lib.freesasa_set_verbosity(2)
-    return (mine, st.TreeAPI(mine)), (ref, st.TreeAPI(ref))
+    yield (mine, st.TreeAPI(mine)), (ref, st.TreeAPI(ref))
+    mine.lib.freesasa_set_verbosity(0)
 
 
 CASES = [
@@ -143,3 +144,28 @@ def test_reference_test_files(both, name):
         (mine_walk, mine_classes), (ref_walk, ref_classes) = trees_for(both, text, options, 7, name.encode())
         assert mine_walk == ref_walk
         assert mine_classes == ref_classes
+
+
+@needs_ref
+def test_write_pdb_is_byte_identical(both, tmp_path):
+    """Row f-4 writer (src/pdb.c:284-375): same bytes as the reference apart from the program name in the first REMARK."""
+    import os
+
+    text = w.pdb_text(400, seed=21, chains=3, models=1, hetatm=3, altloc=0.1).encode()
+    outputs = []
+    for api, tree in both:
+        L = api.lib
+        L.freesasa_write_pdb.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        s = api.from_pdb(text, None, st.INCLUDE_HETATM)
+        rng = np.random.default_rng(5)
+        result, keep = tree.make_result(rng.uniform(0, 1200, size=s.n) * (rng.random(s.n) < 0.5))
+        root = tree.init(result, s, b"w")
+        path = os.path.join(tmp_path, "out.pdb")
+        fp = st._libc.fopen(path.encode(), b"w")
+        assert L.freesasa_write_pdb(fp, root) == 0
+        st._libc.fclose(fp)
+        tree.free(root)
+        outputs.append(open(path, "rb").read().split(b"\n"))
+    assert outputs[0][0].startswith(b"REMARK 999 This PDB file was generated by")
+    assert outputs[0][1:] == outputs[1][1:]
+    assert len(outputs[0]) > 400

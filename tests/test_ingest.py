@@ -37,7 +37,8 @@ needs_ref = pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not b
 def mine():
     api = st.api()
     api.lib.freesasa_set_verbosity(2)  # silent: the tests provoke errors on purpose
-    return api
+    yield api
+    api.lib.freesasa_set_verbosity(0)
 
 
 @pytest.fixture(scope="module")

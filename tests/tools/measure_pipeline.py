@@ -20,32 +20,35 @@ from freesasa_b200 import workloads as w  # noqa: E402
 from oracle import bindings as ob  # noqa: E402
 
 
-def timed(fn, reps):
+def timed(fn, reps, release=None):
+    """Best wall time of ``reps`` calls in ms; every result but the last is handed to ``release``."""
     best, out = 1e30, None
-    for _ in range(reps):
+    for k in range(reps):
+        if out is not None and release:
+            release(out)
         t = time.perf_counter()
         out = fn()
         best = min(best, time.perf_counter() - t)
     return best * 1e3, out
 
 
-def stages(api, text, params, reps, free_between=True):
-    """ms for read / calc / tree / free; the tree's structure area as a checksum."""
-    tree = st.TreeAPI(api)
+def stages(api, text, params, reps):
+    """ms for read / calc / tree / tree free, and the per-atom result."""
     L = api.lib
-    res_p = ctypes.POINTER(api.Result)
-    L.freesasa_calc_structure.restype = res_p
-    t_read, s = timed(lambda: api.from_pdb(text), reps)
-    t_calc, res = timed(lambda: L.freesasa_calc_structure(s.h, ctypes.byref(params)), reps)
-    t_tree, root = timed(lambda: L.freesasa_tree_init(res, s.h, b"pipeline"), reps)
-    total = next(x for x in tree.walk(L.freesasa_node_children(root), 1) if x[1] == st.NODE_STRUCTURE)[3][1] if s.n <= 20000 else None
-    t_free, _ = timed(lambda: None, 1)
+    L.freesasa_calc_structure.restype = ctypes.POINTER(api.Result)
+    L.freesasa_tree_init.restype = ctypes.c_void_p
+    t_read, s = timed(lambda: api.from_pdb(text), reps, lambda x: x.free())
+    t_calc, res = timed(lambda: L.freesasa_calc_structure(s.h, ctypes.byref(params)), reps, L.freesasa_result_free)
+    if not res:
+        raise RuntimeError("freesasa_calc_structure returned NULL")
+    t_tree, root = timed(lambda: L.freesasa_tree_init(res, s.h, b"pipeline"), reps, L.freesasa_node_free)
     t0 = time.perf_counter()
     L.freesasa_node_free(root)
     t_free = (time.perf_counter() - t0) * 1e3
     sasa = np.ctypeslib.as_array(res.contents.sasa, shape=(s.n,)).copy()
+    L.freesasa_result_free(res)
     return {"atoms": s.n, "read_ms": t_read, "calc_ms": t_calc, "tree_ms": t_tree, "tree_free_ms": t_free,
-            "total_ms": t_read + t_calc + t_tree}, sasa, total
+            "total_ms": t_read + t_calc + t_tree}, sasa
 
 
 def main():
@@ -61,10 +64,10 @@ def main():
         case = {"bytes": len(text)}
         for alg, res_n, key in [(fs.LEE_RICHARDS, 100, "LR-100"), (fs.LEE_RICHARDS, 20, "LR-20")]:
             reps = 3 if n_atoms <= 100000 else 1
-            m, sasa_m, _ = stages(mine, text, fs.Parameters(alg, 1.4, res_n, res_n, 1), reps + 2)
+            m, sasa_m = stages(mine, text, fs.Parameters(alg, 1.4, res_n, res_n, 1), reps + 2)
             entry = {"this_repo": m}
             if n_atoms <= 100000 or key == "LR-20":
-                r, sasa_r, _ = stages(ref, text, ob.RefParameters(alg, 1.4, res_n, res_n, threads), 1 if n_atoms > 20000 else reps)
+                r, sasa_r = stages(ref, text, ob.RefParameters(alg, 1.4, res_n, res_n, threads), 1 if n_atoms > 20000 else reps)
                 entry["reference"] = r
                 entry["max_abs_err"] = float(np.abs(sasa_m - sasa_r).max())
                 entry["speedup_total"] = r["total_ms"] / m["total_ms"]
