@@ -302,8 +302,32 @@ static struct shared_text *slurp(FILE *f)
     }
     t->refs = 1;
     if (fseek(f, 0, SEEK_END) != 0 || (t->len = ftell(f)) < 0) {
-        FAIL_MSG("%s", strerror(errno));
-        goto fail;
+        /* not seekable (a pipe: `cat x.pdb | program`).  The reference's ftell()-based range logic degenerates to "read
+         * lines until EOF" there (src/util.c:20-34, src/structure.c:658); do the same: everything up to EOF */
+        size_t cap = 1 << 20, len = 0, n;
+        clearerr(f);
+        if (!(t->data = malloc(cap + 1))) {
+            MEM_FAIL();
+            goto fail;
+        }
+        while ((n = fread(t->data + len, 1, cap - len, f)) > 0) {
+            len += n;
+            if (len == cap) {
+                char *p = realloc(t->data, (cap *= 2) + 1);
+                if (!p) {
+                    MEM_FAIL();
+                    goto fail;
+                }
+                t->data = p;
+            }
+        }
+        if (ferror(f)) {
+            FAIL_MSG("%s", strerror(errno));
+            goto fail;
+        }
+        t->len = (long)len;
+        t->data[len] = '\0';
+        return t;
     }
     rewind(f);
     if (!(t->data = malloc((size_t)t->len + 1))) {

@@ -724,23 +724,31 @@ __constant__ float4 c_cert_points[kCertPoints];   // the probe directions (uploa
 // kCertList = 64, two per lane, kept in registers); then every probe direction — one uniform constant-memory
 // load — is tested against all of them at once and a single vote says whether some neighbour hides its whole
 // patch.  The first patch nobody hides ends the attempt.
+#ifndef FSB200_CERT_VARIANT
+#define FSB200_CERT_VARIANT 1   // 0: lanes = neighbours, loop over the 128 directions; 1: lanes = directions, loop over the caps
+#endif
 template <typename T, bool HAS_T>   // HAS_T: recs hold {dx,dy,dz,t} (S&R); otherwise raw {dx,dy,dz,Ra} (L&R)
-__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list, int nn, float Ri, int lane)
+__device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list, int nn, float Ri, int lane,
+                                               const float4 *__restrict__ dirs)
 {
     const unsigned lt = lanemask_lt();
-    int n_useful = 0;
+    int n_useful = 0, n_wide = 0;
     bool inside = false;
-    // Short list = neighbours whose cap is wider than a patch.  If more than kCertList qualify (dense packing,
-    // explicit hydrogens), the bar is raised to caps at least 20, 35, 50 degrees wider, until they fit: the
-    // widest caps are the ones that hide whole patches anyway.
+    // Short list = neighbours whose cap is wider than a patch, WIDE caps (half-angle > ~50 deg: the bonded and second-
+    // shell neighbours, which hide most of the sphere between them) compacted from the front of the list, the others
+    // from the back, so the coverage loop meets the wide ones first.  If more than kCertList qualify (dense packing,
+    // explicit hydrogens), the bar is raised to caps at least 20, 35, 50 degrees wider, until they fit: the widest caps
+    // are the ones that hide whole patches anyway.
     const float bars[4] = {kCertCos, 0.82412619f, 0.64944805f, 0.43051110f};   // cos(14.5, 34.5, 49.5, 64.5 deg)
+    constexpr float kWide = 0.65f;                                              // cos(49.5 deg)
     for (int attempt = 0; attempt < 4; ++attempt) {
         const float bar = bars[attempt];
+        int n_back = 0;
         n_useful = 0;
         for (int base = 0; base < nn; base += 32) {
             const int j = base + lane;
             float4 e = make_float4(0.f, 0.f, 0.f, 3.0e38f);
-            bool useful = false;
+            bool useful = false, wide = true;
             if (j < nn) {
                 const Rec4<T> r = recs[j];
                 e.x = (float)r.a; e.y = (float)r.b; e.z = (float)r.c;
@@ -753,23 +761,54 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
                 else if (t < d * bar) {                        // cap wide enough for this attempt
                     e.w = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
                     useful = true;
+                    wide = attempt > 0 || t < d * kWide;
                 }
             }
-            const unsigned m = __ballot_sync(kFull, useful);
+            const unsigned mf = __ballot_sync(kFull, useful && wide), mb = __ballot_sync(kFull, useful && !wide);
             if (useful) {
-                const int slot = n_useful + __popc(m & lt);
-                if (slot < kCertList) list[slot] = e;
+                const int slot = wide ? n_useful + __popc(mf & lt) : kCertList - 1 - (n_back + __popc(mb & lt));
+                if (slot >= 0 && slot < kCertList) list[slot] = e;
             }
-            n_useful += __popc(m);
+            n_useful += __popc(mf);
+            n_back += __popc(mb);
         }
+        n_wide = n_useful;
+        n_useful += n_back;
         if (n_useful <= kCertList) break;
     }
     if (__any_sync(kFull, inside)) return true;
     if (n_useful == 0 || n_useful > kCertList) return false;   // nothing to work with / too many for the short list
     __syncwarp();
+#if FSB200_CERT_VARIANT == 1
+    {
+        // lanes = directions (four per lane, read once per atom from the L1-resident table), loop over the caps: one
+        // broadcast shared-memory load per cap serves 128 (direction, cap) tests; the attempt ends as soon as every
+        // direction has found a cap that hides its whole patch.  Same predicate, same expression as variant 0, so
+        // the set of certified atoms is identical.
+        const float4 u0 = __ldg(dirs + lane), u1 = __ldg(dirs + lane + 32), u2 = __ldg(dirs + lane + 64), u3 = __ldg(dirs + lane + 96);
+        bool h0 = false, h1 = false, h2 = false, h3 = false;
+        bool done = false;
+        for (int j = 0; j < n_useful; j += 2) {
+            // entries 0 .. n_wide-1 sit at the front of the list, the others at its back (last one first)
+            const float4 e = list[j < n_wide ? j : kCertList - 1 - (j - n_wide)];
+            const float4 f = j + 1 < n_useful ? list[j + 1 < n_wide ? j + 1 : kCertList - 1 - (j + 1 - n_wide)]
+                                              : make_float4(0.f, 0.f, 0.f, 3.0e38f);
+            h0 = h0 || fmaf(u0.x, e.x, fmaf(u0.y, e.y, u0.z * e.z)) >= e.w || fmaf(u0.x, f.x, fmaf(u0.y, f.y, u0.z * f.z)) >= f.w;
+            h1 = h1 || fmaf(u1.x, e.x, fmaf(u1.y, e.y, u1.z * e.z)) >= e.w || fmaf(u1.x, f.x, fmaf(u1.y, f.y, u1.z * f.z)) >= f.w;
+            h2 = h2 || fmaf(u2.x, e.x, fmaf(u2.y, e.y, u2.z * e.z)) >= e.w || fmaf(u2.x, f.x, fmaf(u2.y, f.y, u2.z * f.z)) >= f.w;
+            h3 = h3 || fmaf(u3.x, e.x, fmaf(u3.y, e.y, u3.z * e.z)) >= e.w || fmaf(u3.x, f.x, fmaf(u3.y, f.y, u3.z * f.z)) >= f.w;
+            if (__all_sync(kFull, h0 && h1 && h2 && h3)) {
+                done = true;
+                break;
+            }
+        }
+        __syncwarp();                                          // the list's memory is reused by the integrators
+        return done;
+    }
+#endif
     const float4 none = make_float4(0.f, 0.f, 0.f, 3.0e38f);
-    const float4 n0 = lane < n_useful ? list[lane] : none;
-    const float4 n1 = lane + 32 < n_useful ? list[lane + 32] : none;
+    const float4 n0 = lane < n_useful ? list[lane < n_wide ? lane : kCertList - 1 - (lane - n_wide)] : none;
+    const float4 n1 = lane + 32 < n_useful ? list[lane + 32 < n_wide ? lane + 32 : kCertList - 1 - (lane + 32 - n_wide)] : none;
     __syncwarp();                                              // the list's memory is reused by the integrators
     if (n_useful <= 32) {
         for (int k = 0; k < kCertPoints; ++k) {
@@ -824,7 +863,7 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
     if (s.R > 0.0) {
         if constexpr (FAST && sizeof(T) == 4) {
             if (args.cert_points != nullptr && nn > 0)
-                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_list, nn, (float)s.R, lane);
+                certified = certify_buried<T, ALG == 1>(wm.recs, wm.cert_list, nn, (float)s.R, lane, args.cert_points);
         }
         if (certified) {
             // area stays 0: proved completely buried

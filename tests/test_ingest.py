@@ -419,3 +419,31 @@ def test_pdb_line_accessor_is_stable(mine):
     t = mine.new()
     t.add_atom(b" CA ", b"ALA", b"   1 ", b"A", 0.0, 0.0, 0.0)
     assert t.atoms()[0][7] is None  # atoms added by hand carry no PDB line (src/structure.c:1199-1206)
+
+
+@needs_ref
+def test_reading_from_a_pipe(mine, ref):
+    """`cat x.pdb | program`: the stream is not seekable; both libraries read up to EOF (the reference by accident of
+    its ftell() arithmetic, src/util.c:20-34)."""
+    text = w.pdb_text(3000, seed=71, chains=2, hetatm=2).encode()  # larger than a pipe buffer
+    snaps = []
+    for api in (mine, ref):
+        import threading
+
+        r, wr = os.pipe()
+
+        def feed():
+            with os.fdopen(wr, "wb") as f:
+                f.write(text)
+
+        t = threading.Thread(target=feed)
+        t.start()
+        st._libc.fdopen.restype = ctypes.c_void_p
+        fp = st._libc.fdopen(r, b"r")
+        h = api.lib.freesasa_structure_from_pdb(fp, None, 0)
+        st._libc.fclose(fp)
+        t.join()
+        assert h
+        snaps.append(snapshot(st.Structure(api, h)))
+    assert snaps[0] == snaps[1]
+    assert snaps[0] == snapshot(mine.from_pdb(text))
