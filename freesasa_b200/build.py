@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libfsb200.so")
 SOURCES = ["api.cu", "cells.cu", "integrate.cu"]
-HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(ROOT, "include", "fsb200.h")]
+HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(CSRC, "cert_dirs.inc"), os.path.join(ROOT, "include", "fsb200.h")]
 HOST_LIB = os.path.join(CSRC, "libfreesasa_b200_host.so")
 HOST_SOURCES = ["host_shim.c", "radii.c", "ingest.c", "areas.c"]
 HOST_HEADERS = [os.path.join(ROOT, "include", "freesasa_b200_host.h"), os.path.join(ROOT, "include", "fsb200.h"),

@@ -24,6 +24,11 @@ using namespace fsb200;
 
 namespace {
 
+// probe directions of the buried-atom certificate: one vector per antipodal pair
+const float kCertDirs[kCertPairs][3] = {
+#include "cert_dirs.inc"
+};
+
 thread_local char g_error[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
@@ -556,13 +561,11 @@ fsb200_ctx *fsb200_ctx_create(int device)
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_status, sizeof(int) * kCtrCount) == cudaSuccess;
-    if (ok) {  // the certificate's probe set: the same patch-ordered golden spiral the S&R path uses, 128 points
-        std::vector<double> pd;
-        std::vector<float4> pf;
-        make_test_points(kCertPoints, pd, pf);
+    if (ok) {  // the certificate's probe set: kCertPairs antipodal pairs (cert_dirs.inc)
+        std::vector<float4> pf(kCertPairs);
+        for (int k = 0; k < kCertPairs; ++k) pf[k] = make_float4(kCertDirs[k][0], kCertDirs[k][1], kCertDirs[k][2], 0.f);
         ok = c->cert_points.ensure(pf.size()) == cudaSuccess &&
-             cudaMemcpy(c->cert_points.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice) == cudaSuccess &&
-             set_cert_points(pf.data()) == 0;
+             cudaMemcpy(c->cert_points.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) {
         fail("could not initialise context on device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
@@ -758,6 +761,17 @@ int fsb200_ctx_unpermute(fsb200_ctx *c, const double *d_sorted, double *d_out, i
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     g_launches += launch_unpermute(c->perm.p, d_sorted, d_out, n_total, st);
     CU(cudaStreamSynchronize(st));
+    return FSB200_SUCCESS;
+}
+
+int fsb200_cert_directions(double *out)
+{
+    if (!out) return fail("fsb200_cert_directions: null output");
+    for (int k = 0; k < kCertPairs; ++k)
+        for (int a = 0; a < 3; ++a) {
+            out[3 * k + a] = (double)kCertDirs[k][a];
+            out[3 * (k + kCertPairs) + a] = -(double)kCertDirs[k][a];
+        }
     return FSB200_SUCCESS;
 }
 

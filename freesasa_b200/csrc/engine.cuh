@@ -28,7 +28,8 @@ constexpr int kRingSlots = 2;               // tiles in flight per CTA
 constexpr int kItemAtoms = 16;              // one work item = up to 16 consecutive atoms of one cell
 constexpr int kTileCap = 640;               // atoms of the 27-cell neighbourhood staged in smem (20 KB)
 constexpr int kNbCap = 160;                 // per-warp neighbour list capacity in smem
-constexpr int kCertPoints = 128;           // probe directions of the buried-atom certificate
+constexpr int kCertPoints = 128;           // probe directions of the buried-atom certificate: kCertPairs antipodal pairs
+constexpr int kCertPairs = kCertPoints / 2;
 constexpr int kCellsPerAtomCap = 2;         // grid budget: cells <= 2*n_k + 64 per structure
 constexpr int kCellsSlack = 64;
 
@@ -103,7 +104,7 @@ struct IntegrateArgs {
     const float4 *points_f;   // SR: unit test points, float
     const double *points_d;   // SR: unit test points, 3*resolution doubles (bit-identical to the reference's)
     int grid_ctas;
-    const float4 *cert_points;  // non-null: use the buried-atom certificate (the directions themselves live in constant memory)
+    const float4 *cert_points;  // non-null: use the buried-atom certificate; kCertPairs unit vectors (the set is these and their negatives)
 };
 
 // cells.cu
@@ -115,7 +116,6 @@ int launch_overflow(const Workspace &ws, const IntegrateArgs &args, int n_overfl
 size_t overflow_scratch_bytes(int n_warps, int list_cap, int precision);
 int overflow_warps(int n_overflow);
 int integrate_grid_ctas(int alg, int precision, int device);
-int set_cert_points(const float4 *host_points);   // kCertPoints probe directions -> constant memory of the current device
 int launch_unpermute(const int *perm, const double *sorted, double *out, int n, cudaStream_t stream);
 
 // ---- small device helpers --------------------------------------------------------------------

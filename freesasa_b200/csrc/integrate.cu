@@ -716,17 +716,17 @@ __device__ __forceinline__ double sr_atom(Rec4<T> *recs, int *cidx, const double
 //     src/sasa_lr.c:389-408; its point count is 0) and so is ours.
 // The test is conservative — a certified atom is always truly buried (never the other way round) — so it
 // changes no result, only the time (tests: certificate on/off give bit-identical arrays).
-constexpr float kCertCos = 0.96814764f;   // cos(14.5 deg)
-constexpr float kCertSin = 0.25038000f;   // sin(14.5 deg)
-__constant__ float4 c_cert_points[kCertPoints];   // the probe directions (uploaded per device by set_cert_points)
+constexpr float kCertCos = 0.97629601f;   // cos(12.5 deg)
+constexpr float kCertSin = 0.21643961f;   // sin(12.5 deg)
 
-// lanes = neighbours.  Neighbours whose cap is wider than a patch are compacted into a short list (at most
-// kCertList = 64, two per lane, kept in registers); then every probe direction — one uniform constant-memory
-// load — is tested against all of them at once and a single vote says whether some neighbour hides its whole
-// patch.  The first patch nobody hides ends the attempt.
-#ifndef FSB200_CERT_VARIANT
-#define FSB200_CERT_VARIANT 1   // 0: lanes = neighbours, loop over the 128 directions; 1: lanes = directions, loop over the caps
-#endif
+// lanes = directions.  The probe set is 64 antipodal pairs (cert_dirs.inc: Lloyd-relaxed, covering radius 12.17 deg);
+// a lane owns two pairs, i.e. four directions, and ONE dot product decides a pair: u.D >= t' hides the patch of u,
+// -(u.D) >= t' hides the patch of -u.  Neighbours whose cap is wider than a patch are compacted into a short list in
+// shared memory (at most kCertList = 64), wide caps first; the loop over the list costs one broadcast load per cap and
+// ends as soon as every direction has found a cap that hides its whole patch.
+//
+// History (profiles/): v1 lanes = directions over ALL neighbours; v2 lanes = neighbours, 128 directions from constant
+// memory with one vote each (1700 warp instructions per atom); this version ~800.
 template <typename T, bool HAS_T>   // HAS_T: recs hold {dx,dy,dz,t} (S&R); otherwise raw {dx,dy,dz,Ra} (L&R)
 __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list, int nn, float Ri, int lane,
                                                const float4 *__restrict__ dirs)
@@ -739,7 +739,7 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     // from the back, so the coverage loop meets the wide ones first.  If more than kCertList qualify (dense packing,
     // explicit hydrogens), the bar is raised to caps at least 20, 35, 50 degrees wider, until they fit: the widest caps
     // are the ones that hide whole patches anyway.
-    const float bars[4] = {kCertCos, 0.82412619f, 0.64944805f, 0.43051110f};   // cos(14.5, 34.5, 49.5, 64.5 deg)
+    const float bars[4] = {kCertCos, 0.84339145f, 0.67559021f, 0.46174861f};   // cos(12.5, 32.5, 47.5, 62.5 deg)
     constexpr float kWide = 0.65f;                                              // cos(49.5 deg)
     for (int attempt = 0; attempt < 4; ++attempt) {
         const float bar = bars[attempt];
@@ -779,52 +779,27 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     if (__any_sync(kFull, inside)) return true;
     if (n_useful == 0 || n_useful > kCertList) return false;   // nothing to work with / too many for the short list
     __syncwarp();
-#if FSB200_CERT_VARIANT == 1
-    {
-        // lanes = directions (four per lane, read once per atom from the L1-resident table), loop over the caps: one
-        // broadcast shared-memory load per cap serves 128 (direction, cap) tests; the attempt ends as soon as every
-        // direction has found a cap that hides its whole patch.  Same predicate, same expression as variant 0, so
-        // the set of certified atoms is identical.
-        const float4 u0 = __ldg(dirs + lane), u1 = __ldg(dirs + lane + 32), u2 = __ldg(dirs + lane + 64), u3 = __ldg(dirs + lane + 96);
-        bool h0 = false, h1 = false, h2 = false, h3 = false;
-        bool done = false;
-        for (int j = 0; j < n_useful; j += 2) {
-            // entries 0 .. n_wide-1 sit at the front of the list, the others at its back (last one first)
-            const float4 e = list[j < n_wide ? j : kCertList - 1 - (j - n_wide)];
-            const float4 f = j + 1 < n_useful ? list[j + 1 < n_wide ? j + 1 : kCertList - 1 - (j + 1 - n_wide)]
-                                              : make_float4(0.f, 0.f, 0.f, 3.0e38f);
-            h0 = h0 || fmaf(u0.x, e.x, fmaf(u0.y, e.y, u0.z * e.z)) >= e.w || fmaf(u0.x, f.x, fmaf(u0.y, f.y, u0.z * f.z)) >= f.w;
-            h1 = h1 || fmaf(u1.x, e.x, fmaf(u1.y, e.y, u1.z * e.z)) >= e.w || fmaf(u1.x, f.x, fmaf(u1.y, f.y, u1.z * f.z)) >= f.w;
-            h2 = h2 || fmaf(u2.x, e.x, fmaf(u2.y, e.y, u2.z * e.z)) >= e.w || fmaf(u2.x, f.x, fmaf(u2.y, f.y, u2.z * f.z)) >= f.w;
-            h3 = h3 || fmaf(u3.x, e.x, fmaf(u3.y, e.y, u3.z * e.z)) >= e.w || fmaf(u3.x, f.x, fmaf(u3.y, f.y, u3.z * f.z)) >= f.w;
-            if (__all_sync(kFull, h0 && h1 && h2 && h3)) {
-                done = true;
-                break;
-            }
+    const float4 u0 = __ldg(dirs + lane), u1 = __ldg(dirs + lane + 32);   // two antipodal pairs per lane, L1-resident table
+    bool p0 = false, m0 = false, p1 = false, m1 = false;                  // patch of +u0, -u0, +u1, -u1 hidden
+    bool done = false;
+    for (int j = 0; j < n_useful; j += 2) {
+        // entries 0 .. n_wide-1 sit at the front of the list, the others at its back (last one first)
+        const float4 e = list[j < n_wide ? j : kCertList - 1 - (j - n_wide)];
+        const float4 f = j + 1 < n_useful ? list[j + 1 < n_wide ? j + 1 : kCertList - 1 - (j + 1 - n_wide)]
+                                          : make_float4(0.f, 0.f, 0.f, 3.0e38f);
+        const float e0 = fmaf(u0.x, e.x, fmaf(u0.y, e.y, u0.z * e.z)), e1 = fmaf(u1.x, e.x, fmaf(u1.y, e.y, u1.z * e.z));
+        const float f0 = fmaf(u0.x, f.x, fmaf(u0.y, f.y, u0.z * f.z)), f1 = fmaf(u1.x, f.x, fmaf(u1.y, f.y, u1.z * f.z));
+        p0 = p0 || e0 >= e.w || f0 >= f.w;
+        m0 = m0 || -e0 >= e.w || -f0 >= f.w;
+        p1 = p1 || e1 >= e.w || f1 >= f.w;
+        m1 = m1 || -e1 >= e.w || -f1 >= f.w;
+        if (__all_sync(kFull, p0 && m0 && p1 && m1)) {
+            done = true;
+            break;
         }
-        __syncwarp();                                          // the list's memory is reused by the integrators
-        return done;
     }
-#endif
-    const float4 none = make_float4(0.f, 0.f, 0.f, 3.0e38f);
-    const float4 n0 = lane < n_useful ? list[lane < n_wide ? lane : kCertList - 1 - (lane - n_wide)] : none;
-    const float4 n1 = lane + 32 < n_useful ? list[lane + 32 < n_wide ? lane + 32 : kCertList - 1 - (lane + 32 - n_wide)] : none;
     __syncwarp();                                              // the list's memory is reused by the integrators
-    if (n_useful <= 32) {
-        for (int k = 0; k < kCertPoints; ++k) {
-            const float4 u = c_cert_points[k];                 // uniform address: constant-cache broadcast
-            const bool c = fmaf(u.x, n0.x, fmaf(u.y, n0.y, u.z * n0.z)) >= n0.w;
-            if (!__any_sync(kFull, c)) return false;
-        }
-    } else {
-        for (int k = 0; k < kCertPoints; ++k) {
-            const float4 u = c_cert_points[k];
-            const bool c = fmaf(u.x, n0.x, fmaf(u.y, n0.y, u.z * n0.z)) >= n0.w ||
-                           fmaf(u.x, n1.x, fmaf(u.y, n1.y, u.z * n1.z)) >= n1.w;
-            if (!__any_sync(kFull, c)) return false;
-        }
-    }
-    return true;
+    return done;
 }
 
 // ---- one atom after its neighbours have been gathered ------------------------------------------------
@@ -1204,10 +1179,6 @@ template <int ALG, typename T> int configure_and_occupancy(int device)
 
 }  // namespace
 
-int set_cert_points(const float4 *host_points)
-{
-    return cudaMemcpyToSymbol(c_cert_points, host_points, sizeof(float4) * kCertPoints) == cudaSuccess ? 0 : -1;
-}
 
 int integrate_grid_ctas(int alg, int precision, int device)
 {

@@ -127,6 +127,9 @@ int fsb200_ctx_neighbour_counts(fsb200_ctx *ctx, int *counts, const double *xyz,
  * reference's golden spiral (src/sasa_sr.c:56-90), bit-identical values, in the engine's patch order.
  * Pure host code: works without a GPU. */
 int fsb200_test_points(int n_points, double *out);
+/* The 128 probe directions of the buried-atom certificate (384 doubles: 64 unit vectors, then their negatives) exactly as
+ * the device uses them, so that a test can measure their covering radius.  Pure host code. */
+int fsb200_cert_directions(double *out);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 """The buried-atom certificate (freesasa_b200/csrc/integrate.cu: certify_buried).
 
-CPU part: the geometric constant it relies on — the 128-point golden spiral covers the sphere with patches
-of angular radius < 14.5 degrees.  GPU part: the certificate never changes a result and only ever fires on
+CPU part: the geometric constant it relies on — the library's 128 probe directions (64 antipodal pairs) cover the
+sphere with patches of angular radius < 12.5 degrees.  GPU part: the certificate never changes a result and only ever fires on
 atoms whose reference area is exactly zero."""
 import math
 import os
@@ -13,7 +13,7 @@ import pytest
 from oracle import bindings as ob
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-RHO_DEG = 14.5
+RHO_DEG = 12.5
 
 
 def _constants():
@@ -27,8 +27,17 @@ def _constants():
 def test_patch_radius_constant_covers_the_sphere():
     cos, sin, n = _constants()
     assert abs(cos - math.cos(math.radians(RHO_DEG))) < 1e-6 and abs(sin - math.sin(math.radians(RHO_DEG))) < 1e-6
-    pts = ob.oracle_test_points(n)  # the same recurrence the engine's host code uses (order is irrelevant here)
-    m = 200_000
+    import ctypes
+
+    import freesasa_b200 as fs
+
+    pts = np.empty((n, 3))
+    lib = fs._engine_lib()
+    lib.fsb200_cert_directions.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    assert lib.fsb200_cert_directions(pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0  # the device's own table
+    assert np.array_equal(pts[: n // 2], -pts[n // 2:])                      # antipodal pairs: one dot product per pair
+    assert np.abs(np.linalg.norm(pts, axis=1) - 1).max() < 2e-7             # unit vectors up to fp32 rounding
+    m = 1_000_000
     probe = ob.oracle_test_points(m)  # a dense deterministic probe set; its own covering radius is ~1.3*sqrt(4pi/m)
     best = np.full(m, -1.0)
     for i in range(0, n, 32):
