@@ -39,10 +39,11 @@ N_SLICES = 100
 PROBE = 1.4
 ALG_BYTES_PER_ATOM = 40.0
 # DRAM traffic of the dominant kernel, from the committed ncu --set full capture of this same command
-# (bench.py --steps 2 --warmup 3): 4.90 MB read + 0.0 KB written per launch for 100k atoms = 49.0 B/atom,
-# i.e. the 32 B/atom sorted double4 records are fetched about once and everything else stays in L2/shared memory.
-NCU_DRAM_BYTES_PER_LAUNCH = 4903936
-NCU_SOURCE = "profiles/r1_12_lr_final.txt"
+# (bench.py --steps 2 --warmup 3): 6.00 MB read + 0.0 KB written per launch for 100k atoms = 60 B/atom,
+# i.e. the 32 B/atom sorted double4 records are fetched about once (plus the item queue, the permutation and the L2-flushed
+# output lines) and everything else stays in L2/shared memory.
+NCU_DRAM_BYTES_PER_LAUNCH = 6001920
+NCU_SOURCE = "profiles/r1_15_lr_cert_antipodal_hybrid.txt"
 METRIC = "atoms/sec (LR n_slices=100)"
 WORKLOAD = "C2: 100k-atom synthetic globular coord array, Lee-Richards n_slices=100, probe 1.4 A"
 
