@@ -28,7 +28,7 @@ from . import workloads  # noqa: F401  (numpy-only synthetic inputs)
 
 __all__ = [
     "LEE_RICHARDS", "SHRAKE_RUPLEY", "FP32", "FP64", "Parameters", "Result", "Engine", "Stats",
-    "available", "calc_coord", "calc_coord_batch", "default_parameters", "library_paths", "workloads",
+    "available", "calc_batch", "calc_coord", "calc_coord_batch", "default_parameters", "library_paths", "workloads",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -237,6 +237,20 @@ def calc_coord_batch(structures: Sequence, parameters: Optional[Parameters] = No
                           Parameters.from_buffer_copy(r.parameters)))
         H.freesasa_result_free(results[k])
     return out
+
+
+def calc_batch(alg: int, structures: Sequence, probe: float = 1.4, resolution: int = 20):
+    """fsb200_calc_batch() of the C ABI (context-free): list of (xyz, radii) -> list of per-atom SASA arrays.
+    Batches of >= 400k atoms are worked through as overlapped sub-batches on two pooled contexts."""
+    L = _engine_lib()
+    rad = [_f64(r) for _, r in structures]
+    xyz = [_f64(x, 3 * r.shape[0]) for (x, _), r in zip(structures, rad)]
+    outs = [np.empty(r.shape[0], dtype=np.float64) for r in rad]
+    counts = (ctypes.c_int * len(rad))(*[int(r.shape[0]) for r in rad])
+    if L.fsb200_calc_batch(int(alg), len(rad), counts, _ptr_array(xyz), _ptr_array(rad), _ptr_array(outs), float(probe),
+                           int(resolution)) != 0:
+        raise RuntimeError("fsb200_calc_batch failed: " + _last_error())
+    return outs
 
 
 # ------------------------------------------------------------------------------------------------------

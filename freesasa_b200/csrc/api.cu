@@ -786,14 +786,72 @@ int fsb200_test_points(int n_points, double *out)
 }
 
 // ---- context-free drop-in entry points ------------------------------------------------------------------
+// Large batches through the context-free entry point are cut into contiguous sub-batches that two pooled contexts
+// (two streams, two sets of device scratch, two pinned staging buffers) work through from two host threads: while one
+// sub-batch is being integrated, the next one is being staged and uploaded and the previous one downloaded, so the
+// PCIe transfers (a third to a half of an end-to-end call on the 1024-structure configuration) hide behind the kernels.
+// Structures are independent, results do not depend on the split.
+constexpr long long kOverlapMinAtoms = 400000;   // below this one pass is cheaper than a second thread
+constexpr long long kOverlapChunkAtoms = 320000; // sub-batch size: ~10 MB up, ~2.5 MB down, a few ms of kernel
+
 int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
                       double *const *sasa, double probe, int resolution)
 {
-    fsb200_ctx *c = pool_acquire();
-    if (!c) return FSB200_FAIL;
-    const int rc = fsb200_ctx_calc_batch(c, alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
-    pool_release(c);
-    return rc;
+    long long total = 0;
+    if (n_struct > 0 && n_atoms)
+        for (int k = 0; k < n_struct; ++k) total += n_atoms[k] > 0 ? n_atoms[k] : 0;
+    if (n_struct < 4 || total < kOverlapMinAtoms || !xyz || !radii || !sasa) {
+        fsb200_ctx *c = pool_acquire();
+        if (!c) return FSB200_FAIL;
+        const int rc = fsb200_ctx_calc_batch(c, alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
+        pool_release(c);
+        return rc;
+    }
+    const long long chunk_atoms = kOverlapChunkAtoms;
+    const int n_workers = 2;   // measured on the 1024-structure configuration: 2, 3 or 4 workers and sub-batches of 100k..640k
+                               // atoms all land within 35.6..37.8 ms (one pass: 57 ms, kernels alone: 25.7 ms)
+    std::vector<int> begin;   // first structure of each sub-batch, plus the end
+    long long acc = 0;
+    begin.push_back(0);
+    for (int k = 0; k < n_struct; ++k) {
+        acc += n_atoms[k] > 0 ? n_atoms[k] : 0;
+        if (acc >= chunk_atoms && k + 1 < n_struct) {
+            begin.push_back(k + 1);
+            acc = 0;
+        }
+    }
+    begin.push_back(n_struct);
+    const int n_chunks = (int)begin.size() - 1;
+    constexpr int kMaxWorkers = 4;
+    fsb200_ctx *ctx[kMaxWorkers] = {nullptr, nullptr, nullptr, nullptr};
+    for (int w = 0; w < n_workers; ++w) {
+        ctx[w] = pool_acquire();
+        if (!ctx[w]) {
+            for (int v = 0; v < w; ++v) pool_release(ctx[v]);
+            return FSB200_FAIL;
+        }
+    }
+    std::atomic<int> next{0};
+    int rc[kMaxWorkers] = {FSB200_SUCCESS, FSB200_SUCCESS, FSB200_SUCCESS, FSB200_SUCCESS};
+    char err[kMaxWorkers][sizeof g_error + 48] = {"", "", "", ""};
+    auto work = [&](int w) {
+        for (int k; rc[w] == FSB200_SUCCESS && (k = next.fetch_add(1)) < n_chunks;) {
+            const int b = begin[k], cnt = begin[k + 1] - b;
+            rc[w] = fsb200_ctx_calc_batch(ctx[w], alg, cnt, n_atoms + b, xyz + b, radii + b, sasa + b, probe, resolution);
+            if (rc[w] != FSB200_SUCCESS) {
+                snprintf(err[w], sizeof err[w], "structures %d..%d: %s", b, b + cnt - 1, g_error);   // g_error is thread-local
+                next.store(n_chunks);                                                                 // stop the other worker too
+            }
+        }
+    };
+    std::vector<std::thread> helpers;
+    for (int w = 1; w < n_workers; ++w) helpers.emplace_back(work, w);
+    work(0);
+    for (auto &h : helpers) h.join();
+    for (int w = 0; w < n_workers; ++w) pool_release(ctx[w]);
+    for (int w = 0; w < n_workers; ++w)
+        if (rc[w] != FSB200_SUCCESS) return fail("%.500s", err[w]);
+    return FSB200_SUCCESS;
 }
 
 int fsb200_lr(double *sasa, const double *xyz, const double *radii, int n, double probe, int n_slices)

@@ -367,3 +367,22 @@ def test_full_size_100k(eng32, totals):
     assert abs(want_sr.sum() - totals["measured"]["globule100k"]["sr1000"]) < 1e-6
     # size-independent properties: isolated far copy changes nothing; total bounded by sum of spheres
     assert (lr >= 0).all() and (lr <= 4 * math.pi * (r + 1.4) ** 2 + 1e-6).all()
+
+
+def test_large_batch_overlapped_on_two_contexts_equals_one_pass(eng32):
+    """fsb200_calc_batch() cuts batches of >= 400k atoms into sub-batches worked through by two contexts from two
+    threads (transfers hidden behind kernels): results must not depend on the split, and errors must surface."""
+    structs = fs.workloads.batch(120, 3000, 5000, seed=5)          # ~480k atoms -> overlapped path
+    assert sum(len(r) for _, r in structs) >= 400000
+    p = params(fs.LEE_RICHARDS, 30)
+    split = fs.calc_coord_batch(structs, p)
+    whole = eng32.calc_batch(fs.LEE_RICHARDS, structs, 1.4, 30)      # explicit context: one pass
+    for a, b in zip(split, whole):
+        np.testing.assert_array_equal(a.sasa, b)
+    k = 77
+    want = ob.oracle_calc(structs[k][0], structs[k][1], ob.LEE_RICHARDS, 1.4, 30)
+    assert maxerr(split[k].sasa, want) < LR_TOL_FP32
+    bad = list(structs)
+    bad[100] = (np.full_like(structs[100][0], np.nan), structs[100][1])
+    with pytest.raises(RuntimeError):
+        fs.calc_coord_batch(bad, p)

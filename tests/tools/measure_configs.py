@@ -64,6 +64,11 @@ def main():
     t, outs = best_of(lambda: eng.calc_batch(0, structs, 1.4, 50), 3)
     st = eng.stats()
     e = {"structures": 1024, "atoms": total, "e2e_ms": t * 1e3, "atoms_per_s": total / t, "device_ms": st["device_ms"], "integrate_ms": st["integrate_ms"]}
+    # the reference-facing batch call (freesasa_calc_coord_batch -> fsb200_calc_batch): sub-batches overlapped on two contexts
+    t2, res2 = best_of(lambda: fs.calc_batch(0, structs, 1.4, 50), 3)
+    e["e2e_overlapped_ms"] = t2 * 1e3
+    e["atoms_per_s_overlapped"] = total / t2
+    e["overlapped_equals_single_pass"] = bool(all(np.array_equal(res2[k], outs[k]) for k in range(1024)))
     if not skip_oracle:
         errs = [float(np.abs(outs[k] - ob.oracle_calc(structs[k][0], structs[k][1], 0, 1.4, 50)).max()) for k in range(0, 1024, 64)]
         e["max_err_sampled_16_structures"] = max(errs)
