@@ -19,7 +19,7 @@ LIB = os.path.join(CSRC, "libfsb200.so")
 SOURCES = ["api.cu", "cells.cu", "integrate.cu"]
 HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(CSRC, "cert_dirs.inc"), os.path.join(ROOT, "include", "fsb200.h")]
 HOST_LIB = os.path.join(CSRC, "libfreesasa_b200_host.so")
-HOST_SOURCES = ["host_shim.c", "radii.c", "ingest.c", "areas.c"]
+HOST_SOURCES = ["host_shim.c", "radii.c", "ingest.c", "areas.c", "workers.c"]
 HOST_HEADERS = [os.path.join(ROOT, "include", "freesasa_b200_host.h"), os.path.join(ROOT, "include", "fsb200.h"),
                 os.path.join(CSRC, "host_internal.h"), os.path.join(CSRC, "radius_tables.inc")]
 
@@ -62,7 +62,7 @@ def build_host_shim(force: bool = False) -> str:
     if force or _stale(HOST_LIB, srcs + HOST_HEADERS + [LIB]):
         cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
         cmd = [cc, "-std=gnu99", "-O2", "-fPIC", "-Wall", "-Wextra", "-shared", "-I", os.path.join(ROOT, "include"),
-               "-o", HOST_LIB, *srcs, "-L", CSRC, "-lfsb200", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic", "-lm"]
+               "-o", HOST_LIB, *srcs, "-L", CSRC, "-lfsb200", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic", "-lm", "-lpthread"]
         subprocess.run(cmd, check=True)
     return HOST_LIB
 

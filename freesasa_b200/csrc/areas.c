@@ -151,34 +151,123 @@ static void block_free(freesasa_node *result_node)
     free(b); /* nodes, areas, strings and the cloned result all live in this allocation */
 }
 
+/* Everything the per-residue-range workers of freesasa_tree_add_result() need. */
+struct build {
+    const freesasa_structure *s;
+    const freesasa_result *result;
+    struct tree_block *b;
+    freesasa_node *res_nodes, *atom_nodes;
+    freesasa_nodearea *res_areas, *atom_areas, *refs;
+    char *pool_res, *pool_atom, *pool_alt; /* 14 B per residue (name 4, number 6, own chain label 4); 5 B and 4 B per atom */
+};
+
+/* Residues [n_res*part/n_parts, n_res*(part+1)/n_parts) and their atoms: nodes, areas, strings, and the slices of the
+ * per-atom tables the block keeps.  Touches only its own slice of every array (first touch in parallel). */
+static void build_part(int part, int n_parts, void *arg)
+{
+    const struct build *q = arg;
+    const freesasa_structure *s = q->s;
+    const int n = s->n, n_res = s->n_res;
+    const int r0 = (int)((long long)n_res * part / n_parts), r1 = (int)((long long)n_res * (part + 1) / n_parts);
+    const int a0 = r0 < n_res ? s->res_first[r0] : n, a1 = r1 < n_res ? s->res_first[r1] : n;
+    int r, i;
+
+    if (r0 >= r1) return;
+    memcpy(q->b->line_at + a0, s->line_at + a0, (size_t)(a1 - a0) * sizeof(long));
+    memcpy(q->b->line_len + a0, s->line_len + a0, (size_t)(a1 - a0));
+    memcpy(q->b->result.sasa + a0, q->result->sasa + a0, (size_t)(a1 - a0) * sizeof(double)); /* freesasa_result_clone() */
+    for (i = a0; i < a1; ++i) {
+        freesasa_node *a = &q->atom_nodes[i];
+        const struct atom_label *l = &s->label[i];
+        char *name = q->pool_atom + 5 * (size_t)i;
+        memcpy(name, l->name, 5);
+        a->name = name;
+        a->type = FREESASA_NODE_ATOM;
+        a->area = &q->atom_areas[i];
+        a->parent = &q->res_nodes[s->res_index[i]];
+        a->children = NULL;
+        a->next = a + 1; /* the last atom of each residue is cut below */
+        a->p.atom.is_polar = s->cls[i] == FREESASA_ATOM_POLAR;
+        a->p.atom.is_bb = freesasa_atom_is_backbone(l->name);
+        a->p.atom.index = i;
+        a->p.atom.radius = s->radius[i];
+        atom_area(a->area, q->result->sasa[i], a->p.atom.is_bb, s->cls[i]); /* name stays NULL, as in src/node.c:269-270 */
+    }
+    for (r = r0; r < r1; ++r) {
+        freesasa_node *res = &q->res_nodes[r];
+        const int first = s->res_first[r], last = r == n_res - 1 ? n - 1 : s->res_first[r + 1] - 1;
+        const struct atom_label *l = &s->label[first];
+        char *str = q->pool_res + 14 * (size_t)r;
+        const char *chain = res->parent->name; /* set by the serial chain pass */
+        freesasa_nodearea *sum = &q->res_areas[r];
+        res->type = FREESASA_NODE_RESIDUE;
+        memcpy(str, l->res_name, 4);
+        memcpy(str + 4, l->res_number, 6);
+        res->name = str;
+        /* an atom reports its own chain label; it differs from the chain node it hangs under only when a chain label
+         * comes back after another one (A, B, A: the second run of A is filed under B, src/structure.c:1303-1325) */
+        if (memcmp(l->chain, chain, 4) != 0) {
+            memcpy(str + 10, l->chain, 4);
+            chain = str + 10;
+        }
+        res->p.residue.number = str + 4;
+        res->p.residue.n_atoms = last - first + 1;
+        res->p.residue.reference = NULL;
+        if (s->res_has_ref[r]) { /* a copy: the tree may outlive the structure (src/node.c:303-315) */
+            q->refs[r] = s->res_ref[r];
+            res->p.residue.reference = &q->refs[r];
+        }
+        res->children = &q->atom_nodes[first];
+        res->area = sum;
+        *sum = freesasa_nodearea_null;
+        sum->name = res->name;
+        for (i = first; i <= last; ++i) {
+            freesasa_node *a = &q->atom_nodes[i];
+            freesasa_add_nodearea(sum, a->area);
+            a->p.atom.res_name = res->name; /* residues are delimited by number and chain only: names may differ inside */
+            if (memcmp(s->label[i].res_name, l->res_name, 4) != 0) {
+                char *alt = q->pool_alt + 4 * (size_t)i;
+                memcpy(alt, s->label[i].res_name, 4);
+                a->p.atom.res_name = alt;
+            }
+            a->p.atom.res_number = str + 4;
+            a->p.atom.chain = chain;
+        }
+        q->atom_nodes[last].next = NULL;
+    }
+}
+
 /* freesasa_tree_add_result(), src/node.c:441-476, with node_structure/node_chain/node_residue/node_atom
- * (src/node.c:214-409) fused into one pass */
+ * (src/node.c:214-409) fused: a serial pass over the chains, one pass over residues and atoms (split over threads for
+ * large structures: every string lives at an index-derived place in the pool, so the parts are independent), then the
+ * chain and structure sums in order */
 int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *s, const char *name)
 {
     const int n = s->n, n_res = s->n_res, n_chains = s->n_chains;
     const size_t n_nodes = 2 + (size_t)n_chains + (size_t)n_res + (size_t)n;
     const size_t name_len = name ? strlen(name) + 1 : 0, cls_len = strlen(s->classifier_name ? s->classifier_name : "") + 1;
     const size_t labels_len = strlen(s->short_labels ? s->short_labels : "") + 1;
-    /* string pool: result name, classifier name, chain labels (twice: structure name and property), per chain 4,
-     * per residue name 4 + number 6 (+ 4 for a chain label of its own, rarely used), per atom name 5 (+ 4 for a residue
-     * name that differs from its residue node's; untouched capacity otherwise) */
-    const size_t pool = name_len + cls_len + 2 * labels_len + 4 * (size_t)n_chains + 14 * (size_t)n_res + 9 * (size_t)n;
+    /* string pool: result name, classifier name, chain labels (twice: structure name and property), 4 per chain; then
+     * the index-addressed regions: 14 per residue, 5 + 4 per atom (the 4: a residue name that differs from the residue
+     * node's — untouched address space otherwise) */
+    const size_t fixed = name_len + cls_len + 2 * labels_len + 4 * (size_t)n_chains;
+    const size_t pool = fixed + 14 * (size_t)n_res + 9 * (size_t)n;
     size_t off_nodes, off_areas, off_refs, off_sasa, off_lines, off_len, off_pool, total;
     char *mem, *str;
     struct tree_block *b;
+    struct build q;
     freesasa_node *nodes, *rnode, *snode, *chain_nodes, *res_nodes, *atom_nodes;
-    freesasa_nodearea *areas, *refs;
-    int c, r, i, n_ref = 0;
+    freesasa_nodearea *areas;
+    int c, r, parts;
 
     assert(tree);
     assert(tree->type == FREESASA_NODE_ROOT);
     if (s->classifier_name == NULL || n == 0) return FAIL_MSG("structure without atoms");
 
-    for (r = 0; r < n_res; ++r) n_ref += s->res_has_ref[r] != 0;
     off_nodes = align8(sizeof(struct tree_block));
     off_areas = off_nodes + n_nodes * sizeof(freesasa_node);
     off_refs = off_areas + n_nodes * sizeof(freesasa_nodearea);
-    off_sasa = off_refs + (size_t)n_ref * sizeof(freesasa_nodearea);
+    off_sasa = off_refs + (size_t)n_res * sizeof(freesasa_nodearea);
     off_lines = off_sasa + (size_t)n * sizeof(double);
     off_len = off_lines + (size_t)n * sizeof(long);
     off_pool = align8(off_len + (size_t)n);
@@ -190,7 +279,6 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
     b = (struct tree_block *)mem;
     nodes = (freesasa_node *)(mem + off_nodes);
     areas = (freesasa_nodearea *)(mem + off_areas);
-    refs = (freesasa_nodearea *)(mem + off_refs);
     str = mem + off_pool;
 
     b->n_atoms = n;
@@ -199,12 +287,8 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
     b->line_at = (long *)(mem + off_lines);
     b->line_len = (unsigned char *)(mem + off_len);
     b->lines = NULL;
-    memcpy(b->line_at, s->line_at, (size_t)n * sizeof(long));
-    memcpy(b->line_len, s->line_len, (size_t)n);
-    /* freesasa_result_clone(), src/freesasa.c:184-205 */
     b->result = *result;
     b->result.sasa = (double *)(mem + off_sasa);
-    memcpy(b->result.sasa, result->sasa, (size_t)n * sizeof(double));
 
     rnode = nodes;
     snode = nodes + 1;
@@ -241,23 +325,6 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
     snode->children = chain_nodes;
     snode->area = &areas[1];
 
-    /* atoms: one pass; residues and chains pick their ranges up afterwards */
-    for (i = 0; i < n; ++i) {
-        freesasa_node *a = &atom_nodes[i];
-        const struct atom_label *l = &s->label[i];
-        freesasa_node *res = &res_nodes[s->res_index[i]];
-        a->type = FREESASA_NODE_ATOM;
-        POOL(a->name, l->name, 5);
-        a->area = &areas[2 + n_chains + n_res + i];
-        a->parent = res;
-        a->children = NULL;
-        a->next = a + 1; /* the last atom of each residue is cut below */
-        a->p.atom.is_polar = s->cls[i] == FREESASA_ATOM_POLAR;
-        a->p.atom.is_bb = freesasa_atom_is_backbone(l->name);
-        a->p.atom.index = i;
-        a->p.atom.radius = s->radius[i];
-        atom_area(a->area, result->sasa[i], a->p.atom.is_bb, s->cls[i]); /* name stays NULL, as in src/node.c:269-270 */
-    }
     /* chains: names and residue ranges first (the residues need their parent), sums afterwards */
     for (c = 0; c < n_chains; ++c) {
         freesasa_node *ch = &chain_nodes[c];
@@ -275,39 +342,32 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
             res_nodes[r].next = r == last_res ? NULL : &res_nodes[r + 1];
         }
     }
-    for (r = 0; r < n_res; ++r) {
-        freesasa_node *res = &res_nodes[r];
-        const int first = s->res_first[r], last = r == n_res - 1 ? n - 1 : s->res_first[r + 1] - 1;
-        const struct atom_label *l = &s->label[first];
-        const char *number, *chain = res->parent->name;
-        freesasa_nodearea *sum = &areas[2 + n_chains + r];
-        res->type = FREESASA_NODE_RESIDUE;
-        POOL(res->name, l->res_name, 4);
-        POOL(number, l->res_number, 6);
-        /* an atom reports its own chain label; it differs from the chain node it hangs under only when a chain label
-         * comes back after another one (A, B, A: the second run of A is filed under B, src/structure.c:1303-1325) */
-        if (memcmp(l->chain, chain, 4) != 0) POOL(chain, l->chain, 4);
-        res->p.residue.number = number;
-        res->p.residue.n_atoms = last - first + 1;
-        res->p.residue.reference = NULL;
-        if (s->res_has_ref[r]) { /* a copy: the tree may outlive the structure (src/node.c:303-315) */
-            *refs = s->res_ref[r];
-            res->p.residue.reference = refs++;
-        }
-        res->children = &atom_nodes[first];
-        res->area = sum;
-        *sum = freesasa_nodearea_null;
-        sum->name = res->name;
-        for (i = first; i <= last; ++i) {
-            freesasa_node *a = &atom_nodes[i];
-            freesasa_add_nodearea(sum, a->area);
-            a->p.atom.res_name = res->name; /* residues are delimited by number and chain only: names may differ inside */
-            if (memcmp(s->label[i].res_name, l->res_name, 4) != 0) POOL(a->p.atom.res_name, s->label[i].res_name, 4);
-            a->p.atom.res_number = number;
-            a->p.atom.chain = chain;
-        }
-        atom_nodes[last].next = NULL;
+#undef POOL
+    assert((size_t)(str - (mem + off_pool)) <= fixed);
+
+    q.s = s;
+    q.result = result;
+    q.b = b;
+    q.res_nodes = res_nodes;
+    q.atom_nodes = atom_nodes;
+    q.res_areas = &areas[2 + n_chains];
+    q.atom_areas = &areas[2 + n_chains + n_res];
+    q.refs = (freesasa_nodearea *)(mem + off_refs);
+    q.pool_res = mem + off_pool + fixed;
+    q.pool_atom = q.pool_res + 14 * (size_t)n_res;
+    q.pool_alt = q.pool_atom + 5 * (size_t)n;
+    {
+        /* FREESASA_B200_PARALLEL_MIN_ATOMS: test hook, lets the test-suite drive small structures through the threaded build */
+        const char *env = getenv("FREESASA_B200_PARALLEL_MIN_ATOMS");
+        const int min_atoms = env ? atoi(env) : 20000, per_part = min_atoms / 2 > 16 ? min_atoms / 2 : 16;
+        parts = n >= min_atoms ? fsb_hardware_threads() : 1;
+        if (parts > n / per_part) parts = n / per_part > 0 ? n / per_part : 1;
     }
+    if (parts > 1)
+        fsb_parallel_run(parts, build_part, &q);
+    else
+        build_part(0, 1, &q);
+
     for (c = 0; c < n_chains; ++c) {
         freesasa_node *ch = &chain_nodes[c], *res;
         *ch->area = freesasa_nodearea_null;
@@ -317,8 +377,6 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
     *snode->area = freesasa_nodearea_null;
     snode->area->name = snode->name;
     for (c = 0; c < n_chains; ++c) freesasa_add_nodearea(snode->area, chain_nodes[c].area);
-#undef POOL
-    assert((size_t)(str - (mem + off_pool)) <= pool);
 
     /* prepend to the root's list (src/node.c:467-468) */
     rnode->next = tree->children;

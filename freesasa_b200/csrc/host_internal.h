@@ -12,6 +12,13 @@ int fsb_report(int code, const char *where, int line, const char *fmt, ...)
     __attribute__((format(printf, 4, 5)))
 #endif
     ;
+/* per-thread message capture (see fsb_report): while fsb_capture_current is set, messages are appended to it */
+struct fsb_capture {
+    char *text;
+    size_t len, cap;
+};
+extern __thread struct fsb_capture *fsb_capture_current;
+void fsb_capture_flush(struct fsb_capture *c); /* writes the captured text to the error stream and empties the buffer */
 #define FAIL_MSG(...) fsb_report(FREESASA_FAIL, __FILE__, __LINE__, __VA_ARGS__)
 #define WARN_MSG(...) fsb_report(FREESASA_WARN, NULL, 0, __VA_ARGS__)
 #define MEM_FAIL() FAIL_MSG("Out of memory")
@@ -27,6 +34,10 @@ static inline int fsb_token(const char *s, const char **begin)
     *begin = p;
     return (int)(q - p);
 }
+
+/* workers.c */
+int fsb_hardware_threads(void);
+void fsb_parallel_run(int n_parts, void (*fn)(int part, int n_parts, void *arg), void *arg);
 
 /* ---- structure storage (ingest.c), shared with the result tree (areas.c) --------------------------------------- */
 #define LINE_MAX_STRL 120 /* PDB_MAX_LINE_STRL, src/pdb.h:22: fgets() buffer of the reference, longer lines are split */

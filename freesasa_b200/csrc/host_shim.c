@@ -46,20 +46,53 @@ void freesasa_set_err_out(FILE *fp)
 }
 FILE *freesasa_get_err_out(void) { return errlog; }
 
+/* Messages of worker threads (parallel PDB reading) are captured per worker and replayed in input order, so that what
+ * reaches the error stream is exactly what a serial run prints. */
+__thread struct fsb_capture *fsb_capture_current = NULL;
+
+void fsb_capture_flush(struct fsb_capture *c)
+{
+    if (c->len) {
+        FILE *fp = errlog ? errlog : stderr;
+        fwrite(c->text, 1, c->len, fp);
+        fflush(fp);
+    }
+    free(c->text);
+    c->text = NULL;
+    c->len = c->cap = 0;
+}
+
 int fsb_report(int code, const char *where, int line, const char *fmt, ...)
 {
     va_list ap;
     FILE *fp = errlog ? errlog : stderr;
+    char buf[1024];
+    int n;
     if (verbosity == FREESASA_V_SILENT) return code;
     if (code == FREESASA_WARN && verbosity == FREESASA_V_NOWARNINGS) return code;
     if (where)
-        fprintf(fp, "%s:%s:%d: %s: ", prog, where, line, code == FREESASA_WARN ? "warning" : "error");
+        n = snprintf(buf, sizeof buf, "%s:%s:%d: %s: ", prog, where, line, code == FREESASA_WARN ? "warning" : "error");
     else
-        fprintf(fp, "%s: %s: ", prog, code == FREESASA_WARN ? "warning" : "error");
+        n = snprintf(buf, sizeof buf, "%s: %s: ", prog, code == FREESASA_WARN ? "warning" : "error");
     va_start(ap, fmt);
-    vfprintf(fp, fmt, ap);
+    n += vsnprintf(buf + n, sizeof buf - (size_t)n, fmt, ap);
     va_end(ap);
-    fputc('\n', fp);
+    if (n > (int)sizeof buf - 2) n = (int)sizeof buf - 2;
+    buf[n++] = '\n';
+    if (fsb_capture_current) {
+        struct fsb_capture *c = fsb_capture_current;
+        if (c->len + (size_t)n > c->cap) {
+            const size_t cap = 2 * c->cap + (size_t)n + 256;
+            char *p = realloc(c->text, cap);
+            if (!p) return code;
+            c->text = p;
+            c->cap = cap;
+        }
+        memcpy(c->text + c->len, buf, (size_t)n);
+        c->len += (size_t)n;
+        return code;
+    }
+    fwrite(buf, 1, (size_t)n, fp);
     fflush(fp);
     return code;
 }

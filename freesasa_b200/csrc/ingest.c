@@ -32,6 +32,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 
 int fsb_classifier_row(const freesasa_classifier *c, const char *res_name, const char *atom_name);
@@ -291,6 +292,57 @@ int freesasa_structure_add_atom(freesasa_structure *structure, const char *atom_
 }
 
 /* ---- PDB text ---------------------------------------------------------------------------------------- */
+/* Large regular files are read in slices by several threads (pread: the copy out of the page cache and the first touch
+ * of the destination pages are the cost, and both parallelise).  Returns the bytes read or -1 to ask for a plain fread. */
+#define SLURP_PARALLEL_MIN_BYTES (4L << 20)
+struct slice_job {
+    int fd;
+    char *dst;
+    long offset, bytes, got;
+};
+static void *slice_read(void *arg)
+{
+    struct slice_job *j = arg;
+    j->got = 0;
+    while (j->got < j->bytes) {
+        const ssize_t n = pread(j->fd, j->dst + j->got, (size_t)(j->bytes - j->got), (off_t)(j->offset + j->got));
+        if (n <= 0) break;
+        j->got += n;
+    }
+    return NULL;
+}
+static long slurp_parallel(FILE *f, char *dst, long len)
+{
+    struct slice_job job[16];
+    pthread_t thread[16];
+    const int fd = fileno(f);
+    int n = fsb_hardware_threads(), k, started = 0;
+    long total = 0;
+    if (fd < 0 || n < 2) return -1;
+    if (n > 16) n = 16;
+    if (n > len / (1L << 20)) n = (int)(len / (1L << 20));
+    if (n < 2) return -1;
+    for (k = 0; k < n; ++k) {
+        job[k].fd = fd;
+        job[k].offset = len * k / n;
+        job[k].bytes = len * (k + 1) / n - job[k].offset;
+        job[k].dst = dst + job[k].offset;
+        job[k].got = 0;
+    }
+    for (k = 1; k < n; ++k) {
+        if (pthread_create(&thread[k], NULL, slice_read, &job[k]) != 0) break;
+        ++started;
+    }
+    slice_read(&job[0]);
+    for (k = started + 1; k < n; ++k) slice_read(&job[k]);
+    for (k = 1; k <= started; ++k) pthread_join(thread[k], NULL);
+    for (k = 0; k < n; ++k) {
+        if (job[k].got != job[k].bytes) return -1; /* short read (not a regular file?): let fread sort it out */
+        total += job[k].got;
+    }
+    return total;
+}
+
 /* the whole stream in one read (the reference measures the file with fseek/ftell too, src/util.c:20-34) */
 static struct shared_text *slurp(FILE *f)
 {
@@ -334,10 +386,17 @@ static struct shared_text *slurp(FILE *f)
         MEM_FAIL();
         goto fail;
     }
-    got = (long)fread(t->data, 1, (size_t)t->len, f);
-    if (ferror(f)) {
-        FAIL_MSG("%s", strerror(errno));
-        goto fail;
+    got = -1;
+    if (t->len >= SLURP_PARALLEL_MIN_BYTES) got = slurp_parallel(f, t->data, t->len);
+    if (got < 0) { /* small file, or the descriptor could not be read in slices: one fread */
+        rewind(f);
+        got = (long)fread(t->data, 1, (size_t)t->len, f);
+        if (ferror(f)) {
+            FAIL_MSG("%s", strerror(errno));
+            goto fail;
+        }
+    } else {
+        fseek(f, 0, SEEK_END); /* where a full fread leaves the stream */
     }
     t->len = got;
     t->data[got] = '\0';
@@ -472,34 +531,28 @@ static inline int memo_row(struct memo *m, const freesasa_classifier *classifier
     return m->row[slot];
 }
 
-/* from_pdb_impl(), src/structure.c:638-721, on the byte range [begin, end] of the text */
-static freesasa_structure *from_range(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
-                                      int options)
+/* What a pass over a byte range saw besides atoms. */
+struct scan_info {
+    int saw_model, model; /* last MODEL record (only looked at without FREESASA_JOIN_MODELS) */
+    int hit_endmdl;       /* stopped at an ENDMDL record */
+    int odd_lines;        /* a line longer than the reference's fgets() buffer, or one with an embedded NUL */
+};
+
+/* The line loop of from_pdb_impl(), src/structure.c:658-707, over [begin, end] of the text, appending to `s`.  Starts
+ * with "no alternate location seen".  Returns FREESASA_SUCCESS or FREESASA_FAIL (message already reported). */
+static int parse_lines(freesasa_structure *s, const struct shared_text *t, long begin, long end,
+                       const freesasa_classifier *classifier, int options, struct memo *memo, struct scan_info *info)
 {
-    freesasa_structure *s = freesasa_structure_new();
     const freesasa_classifier *cl = classifier ? classifier : &freesasa_default_classifier;
-    struct memo *memo = calloc(1, sizeof *memo);
     char the_alt = ' ';
     long pos = begin, raw, len;
 
-    if (s == NULL || memo == NULL) {
-        free(memo);
-        freesasa_structure_free(s);
-        return NULL;
-    }
-    s->text = (struct shared_text *)t;
-    __atomic_add_fetch(&s->text->refs, 1, __ATOMIC_RELAXED);
-    /* an atom needs a line of at least 54 characters: size every array once, no reallocation while reading (untouched
-     * capacity costs address space only) */
-    {
-        const long span = (end < t->len ? end : t->len) - begin;
-        if (span > 0 && reserve_atoms(s, (int)(span / 54) + 1)) goto fail;
-    }
     while (pos < t->len) {
         const char *l = t->data + pos;
         len = next_line(t, pos, &raw);
         pos += raw;
         if (pos > end) break;
+        if (len != raw || (raw == LINE_MAX_STRL - 1 && l[raw - 1] != '\n')) info->odd_lines = 1;
 
         if (is_atom_line(l, len, options)) {
             struct atom_label a;
@@ -526,7 +579,7 @@ static freesasa_structure *from_range(const struct shared_text *t, long begin, l
                 continue;
 
             /* freesasa_pdb_get_coord(), src/pdb.c:176-197 */
-            if (len < 54) goto fail;
+            if (len < 54) return FREESASA_FAIL;
             if (!strict_coords(l + 30, v) && !fast_coords(l + 30, 24, v)) {
                 char section[25];
                 memcpy(section, l + 30, 24);
@@ -535,13 +588,12 @@ static freesasa_structure *from_range(const struct shared_text *t, long begin, l
                     char copy[LINE_MAX_STRL];
                     memcpy(copy, l, (size_t)len);
                     copy[len] = '\0';
-                    FAIL_MSG("could not read coordinates from line '%s'", copy);
-                    goto fail;
+                    return FAIL_MSG("could not read coordinates from line '%s'", copy);
                 }
             }
 
             ret = add_atom(s, &a, v, classifier, options, l, (size_t)len, memo_row(memo, cl, &a));
-            if (ret == FREESASA_FAIL) goto fail;
+            if (ret == FREESASA_FAIL) return FREESASA_FAIL;
             if (ret == FREESASA_WARN) continue;
 
             if (options & FREESASA_RADIUS_FROM_OCCUPANCY) {
@@ -549,10 +601,10 @@ static freesasa_structure *from_range(const struct shared_text *t, long begin, l
                 char buf[8];
                 float occ;
                 long w = len - 54 < 6 ? len - 54 : 6;
-                if (len < 55) goto fail;
+                if (len < 55) return FREESASA_FAIL;
                 memcpy(buf, l + 54, (size_t)w);
                 buf[w] = '\0';
-                if (sscanf(buf, "%f", &occ) != 1) goto fail;
+                if (sscanf(buf, "%f", &occ) != 1) return FREESASA_FAIL;
                 s->radius[s->n - 1] = occ;
             }
         }
@@ -562,11 +614,312 @@ static freesasa_structure *from_range(const struct shared_text *t, long begin, l
                 char rest[LINE_MAX_STRL];
                 memcpy(rest, l + 10, (size_t)(len - 10));
                 rest[len - 10] = '\0';
-                sscanf(rest, "%d", &s->model);
+                if (sscanf(rest, "%d", &info->model) == 1) info->saw_model = 1;
             }
-            if (len >= 6 && memcmp(l, "ENDMDL", 6) == 0) break;
+            if (len >= 6 && memcmp(l, "ENDMDL", 6) == 0) {
+                info->hit_endmdl = 1;
+                break;
+            }
         }
     }
+    return FREESASA_SUCCESS;
+}
+
+static freesasa_structure *fragment_new(const struct shared_text *t, long span)
+{
+    freesasa_structure *s = freesasa_structure_new();
+    if (s == NULL) return NULL;
+    s->text = (struct shared_text *)t;
+    __atomic_add_fetch(&s->text->refs, 1, __ATOMIC_RELAXED);
+    /* an atom needs a line of at least 54 characters: size every array once, no reallocation while reading (untouched
+     * capacity costs address space only) */
+    if (span > 0 && reserve_atoms(s, (int)(span / 54) + 1)) {
+        freesasa_structure_free(s);
+        return NULL;
+    }
+    return s;
+}
+
+/* ---- parallel reading -------------------------------------------------------------------------------------
+ * A large range is cut at line boundaries into one chunk per thread; every chunk is parsed into a private fragment
+ * (same code as the serial reader, messages captured), then the fragments are concatenated in order.  What makes the
+ * result IDENTICAL to a serial pass:
+ *   - "first alternate location wins" carries state from line to line: a chunk may only start right after an atom
+ *     line that is kept and has a blank alternate-location column, where that state is known to be "none";
+ *   - residues and chains are re-derived at the seams with the serial rules (a residue continues across a seam when
+ *     number and chain agree; a chain label is registered the first time it appears);
+ *   - MODEL numbers: the last MODEL record wins; ENDMDL: every chunk after the first one that met it is discarded;
+ *   - messages are replayed in chunk order up to the first failure;
+ *   - anything odd (over-long lines, NUL bytes, no safe cut found) falls back to the serial reader.
+ */
+#define PARALLEL_MIN_BYTES (1L << 20)
+#define PARALLEL_MAX_THREADS 16
+
+struct chunk_job {
+    const struct shared_text *t;
+    long begin, end;
+    const freesasa_classifier *classifier;
+    int options;
+    freesasa_structure *frag;
+    struct scan_info info;
+    struct fsb_capture messages;
+    int status;
+    /* phase 2 */
+    freesasa_structure *dst;
+    int atom_offset, res_offset;
+};
+
+static long n_parallel_reads; /* test hook: how many ranges went through the parallel reader */
+long fsb_ingest_parallel_reads(void) { return __atomic_load_n(&n_parallel_reads, __ATOMIC_RELAXED); }
+
+static void *chunk_parse(void *arg)
+{
+    struct chunk_job *j = arg;
+    struct memo *memo = calloc(1, sizeof *memo);
+    fsb_capture_current = &j->messages;
+    j->frag = fragment_new(j->t, j->end - j->begin);
+    if (j->frag == NULL || memo == NULL)
+        j->status = FREESASA_FAIL;
+    else
+        j->status = parse_lines(j->frag, j->t, j->begin, j->end, j->classifier, j->options, memo, &j->info);
+    fsb_capture_current = NULL;
+    free(memo);
+    return NULL;
+}
+
+static void *chunk_copy(void *arg)
+{
+    struct chunk_job *j = arg;
+    const freesasa_structure *f = j->frag;
+    freesasa_structure *d = j->dst;
+    const int o = j->atom_offset, n = f->n;
+    int i;
+    memcpy(d->coord.xyz + 3 * (size_t)o, f->coord.xyz, 3 * (size_t)n * sizeof(double));
+    memcpy(d->radius + o, f->radius, (size_t)n * sizeof(double));
+    memcpy(d->label + o, f->label, (size_t)n * sizeof(struct atom_label));
+    memcpy(d->cls + o, f->cls, (size_t)n);
+    memcpy(d->line_at + o, f->line_at, (size_t)n * sizeof(long));
+    memcpy(d->line_len + o, f->line_len, (size_t)n);
+    for (i = 0; i < n; ++i) d->res_index[o + i] = f->res_index[i] + j->res_offset;
+    return NULL;
+}
+
+
+/* First position >= from where a chunk may start (see above), or -1 if none before `limit`. */
+static long safe_cut(const struct shared_text *t, long from, long limit, int options)
+{
+    long pos = from, raw, len;
+    const char *nl = memchr(t->data + pos, '\n', (size_t)(limit - pos));
+    int budget = 4096;
+    if (!nl) return -1;
+    pos = nl - t->data + 1; /* a line start */
+    while (pos < limit && budget-- > 0) {
+        const char *l = t->data + pos;
+        len = next_line(t, pos, &raw);
+        pos += raw;
+        if (len != raw || (raw == LINE_MAX_STRL - 1 && l[raw - 1] != '\n')) return -1;
+        if (is_atom_line(l, len, options) && !(is_hydrogen(l, len) && !(options & FREESASA_INCLUDE_HYDROGEN)) && len > 16 &&
+            l[16] == ' ')
+            return pos;
+    }
+    return -1;
+}
+
+/* Returns 1 and sets *out (NULL on a reported failure) if the range was read in parallel, 0 to ask for the serial reader. */
+static int from_range_parallel(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
+                               int options, freesasa_structure **out)
+{
+    struct chunk_job job[PARALLEL_MAX_THREADS];
+    pthread_t thread[PARALLEL_MAX_THREADS];
+    const long stop = end < t->len ? end : t->len, span = stop - begin;
+    int n_threads = fsb_hardware_threads(), n_jobs = 0, k, used, failed = -1, started;
+    freesasa_structure *s = NULL;
+    long cut = begin;
+
+    {
+        /* FREESASA_B200_PARALLEL_MIN_BYTES: test hook, lets the test-suite drive small inputs through this path */
+        const char *env = getenv("FREESASA_B200_PARALLEL_MIN_BYTES");
+        const long min_bytes = env ? atol(env) : PARALLEL_MIN_BYTES, per_thread = min_bytes / 4 > 256 ? min_bytes / 4 : 256;
+        if (span < min_bytes || n_threads < 2) return 0;
+        if (n_threads > span / per_thread) n_threads = (int)(span / per_thread);
+    }
+    memset(job, 0, sizeof job);
+    for (k = 0; k < n_threads; ++k) {
+        long next = k == n_threads - 1 ? stop : safe_cut(t, begin + span * (k + 1) / n_threads, stop, options);
+        if (next < 0) next = stop; /* no safe cut: this chunk takes the rest */
+        if (next <= cut) continue;
+        job[n_jobs].t = t;
+        job[n_jobs].begin = cut;
+        /* the serial loop stops at the first line that ENDS beyond `end`; chunk ends are line starts, so the last byte
+         * of a chunk's last line is next - 1 */
+        job[n_jobs].end = next == stop ? end : next;
+        job[n_jobs].classifier = classifier;
+        job[n_jobs].options = options;
+        ++n_jobs;
+        cut = next;
+        if (cut >= stop) break;
+    }
+    if (n_jobs < 2) return 0;
+
+    started = 0;
+    for (k = 1; k < n_jobs; ++k) {
+        if (pthread_create(&thread[k], NULL, chunk_parse, &job[k]) != 0) break;
+        ++started;
+    }
+    chunk_parse(&job[0]);
+    for (k = started + 1; k < n_jobs; ++k) chunk_parse(&job[k]); /* threads that could not be created: do it here */
+    for (k = 1; k <= started; ++k) pthread_join(thread[k], NULL);
+
+    __atomic_add_fetch(&n_parallel_reads, 1, __ATOMIC_RELAXED);
+    /* how many chunks count: up to the first failure or ENDMDL; odd lines anywhere -> serial reader decides */
+    used = n_jobs;
+    for (k = 0; k < n_jobs; ++k) {
+        if (job[k].info.odd_lines) goto serial;
+        if (job[k].status != FREESASA_SUCCESS) {
+            failed = k;
+            used = k + 1;
+            break;
+        }
+        if (job[k].info.hit_endmdl) {
+            used = k + 1;
+            break;
+        }
+    }
+    for (k = 0; k < used; ++k) fsb_capture_flush(&job[k].messages);
+    *out = NULL;
+    if (failed < 0) {
+        int total = 0, n_res = 0;
+        for (k = 0; k < used; ++k) total += job[k].frag->n;
+        if (total == 0) {
+            FAIL_MSG("input had no valid ATOM or HETATM lines");
+            failed = used;
+        } else if ((s = fragment_new(t, 0)) == NULL || reserve_atoms(s, total)) {
+            failed = used;
+        } else {
+            /* seams: residue continuation, chain registration, offsets */
+            const struct atom_label *prev = NULL;
+            int atoms = 0;
+            for (k = 0; k < used; ++k) {
+                const freesasa_structure *f = job[k].frag;
+                int r, c, merged;
+                if (f->classifier_name && !s->classifier_name) {
+                    s->classifier_name = strdup(f->classifier_name);
+                    s->last_classifier = f->last_classifier;
+                }
+                if (job[k].info.saw_model) s->model = job[k].info.model;
+                if (f->n == 0) continue;
+                merged = prev && !(memcmp(f->label[0].res_number, prev->res_number, sizeof prev->res_number) ||
+                                   memcmp(f->label[0].chain, prev->chain, sizeof prev->chain));
+                job[k].dst = s;
+                job[k].atom_offset = atoms;
+                job[k].res_offset = n_res - (merged ? 1 : 0);
+                if (n_res + f->n_res > s->cap_res) {
+                    const int cap = 2 * (n_res + f->n_res) + 256;
+                    void *p;
+                    if (!(p = realloc(s->res_first, (size_t)cap * sizeof(int)))) goto nomem;
+                    s->res_first = p;
+                    if (!(p = realloc(s->res_ref, (size_t)cap * sizeof(freesasa_nodearea)))) goto nomem;
+                    s->res_ref = p;
+                    if (!(p = realloc(s->res_has_ref, (size_t)cap))) goto nomem;
+                    s->res_has_ref = p;
+                    s->cap_res = cap;
+                }
+                for (r = merged ? 1 : 0; r < f->n_res; ++r) {
+                    s->res_first[n_res] = f->res_first[r] + atoms;
+                    s->res_ref[n_res] = f->res_ref[r];
+                    s->res_has_ref[n_res] = f->res_has_ref[r];
+                    ++n_res;
+                }
+                for (c = 0; c < f->n_chains; ++c) {
+                    int known = 0, q;
+                    for (q = 0; q < s->n_chains && !known; ++q) known = memcmp(s->chain_label[q], f->chain_label[c], 4) == 0;
+                    if (known) continue;
+                    if (s->n_chains == s->cap_chains) {
+                        const int cap = s->cap_chains ? 2 * s->cap_chains : 64;
+                        void *p;
+                        if (!(p = realloc(s->chain_label, (size_t)cap * 4))) goto nomem;
+                        s->chain_label = p;
+                        if (!(p = realloc(s->short_labels, (size_t)cap + 1))) goto nomem;
+                        s->short_labels = p;
+                        if (!(p = realloc(s->chain_first, (size_t)cap * sizeof(int)))) goto nomem;
+                        s->chain_first = p;
+                        s->cap_chains = cap;
+                    }
+                    memcpy(s->chain_label[s->n_chains], f->chain_label[c], 4);
+                    s->short_labels[s->n_chains] = f->chain_label[c][0];
+                    s->short_labels[s->n_chains + 1] = '\0';
+                    s->chain_first[s->n_chains] = f->chain_first[c] + atoms;
+                    ++s->n_chains;
+                }
+                prev = &f->label[f->n - 1];
+                atoms += f->n;
+            }
+            s->n_res = n_res;
+            s->n = s->coord.n = total;
+            /* phase 2: every fragment is copied into place by its own thread (first touch of the final arrays in parallel) */
+            started = 0;
+            for (k = 1; k < used; ++k) {
+                if (job[k].dst == NULL) continue;
+                if (pthread_create(&thread[k], NULL, chunk_copy, &job[k]) != 0) {
+                    chunk_copy(&job[k]);
+                    thread[k] = 0;
+                } else {
+                    ++started;
+                }
+            }
+            if (job[0].dst) chunk_copy(&job[0]);
+            for (k = 1; k < used; ++k)
+                if (job[k].dst && thread[k]) pthread_join(thread[k], NULL);
+        }
+    }
+    if (failed >= 0) {
+        FAIL_MSG("%s", "");
+        freesasa_structure_free(s);
+        s = NULL;
+    }
+    for (k = 0; k < n_jobs; ++k) {
+        free(job[k].messages.text);
+        freesasa_structure_free(job[k].frag);
+    }
+    *out = s;
+    return 1;
+nomem:
+    MEM_FAIL();
+    failed = used;
+    FAIL_MSG("%s", "");
+    freesasa_structure_free(s);
+    for (k = 0; k < n_jobs; ++k) {
+        free(job[k].messages.text);
+        freesasa_structure_free(job[k].frag);
+    }
+    *out = NULL;
+    return 1;
+serial:
+    for (k = 0; k < n_jobs; ++k) {
+        free(job[k].messages.text);
+        freesasa_structure_free(job[k].frag);
+    }
+    return 0;
+}
+
+/* from_pdb_impl(), src/structure.c:638-721, on the byte range [begin, end] of the text */
+static freesasa_structure *from_range(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
+                                      int options)
+{
+    freesasa_structure *s = NULL;
+    struct memo *memo;
+    struct scan_info info = {0, 0, 0, 0};
+
+    if (from_range_parallel(t, begin, end, classifier, options, &s)) return s;
+    s = fragment_new(t, (end < t->len ? end : t->len) - begin);
+    memo = calloc(1, sizeof *memo);
+    if (s == NULL || memo == NULL) {
+        free(memo);
+        freesasa_structure_free(s);
+        return NULL;
+    }
+    if (parse_lines(s, t, begin, end, classifier, options, memo, &info)) goto fail;
+    if (info.saw_model) s->model = info.model;
     if (s->n == 0) {
         FAIL_MSG("input had no valid ATOM or HETATM lines");
         goto fail;

@@ -169,3 +169,30 @@ def test_write_pdb_is_byte_identical(both, tmp_path):
     assert outputs[0][0].startswith(b"REMARK 999 This PDB file was generated by")
     assert outputs[0][1:] == outputs[1][1:]
     assert len(outputs[0]) > 400
+
+
+@needs_ref
+def test_threaded_tree_build_is_identical(both):
+    """Structures of >= 20 000 atoms are built by several threads (areas.c: build_part); forced on for small ones through
+    the test hook.  Every thread count gives the reference's tree, bit for bit."""
+    import os
+
+    from tests.test_ingest import EDGE_TEXTS
+
+    texts = [w.pdb_text(1200, seed=31, chains=5, hetatm=4, unknown=0.1).encode(), EDGE_TEXTS["chain_returns"].encode() * 7,
+             (EDGE_TEXTS["nucleic"] * 9).encode()]
+    old = {k: os.environ.get(k) for k in ("FREESASA_B200_PARALLEL_MIN_ATOMS", "FREESASA_B200_THREADS")}
+    try:
+        os.environ["FREESASA_B200_PARALLEL_MIN_ATOMS"] = "1"
+        for threads in (2, 3, 8, 16):
+            os.environ["FREESASA_B200_THREADS"] = str(threads)
+            for k, text in enumerate(texts):
+                (mine_walk, mine_classes), (ref_walk, ref_classes) = trees_for(both, text, st.INCLUDE_HETATM, 300 + k)
+                assert mine_walk == ref_walk
+                assert mine_classes == ref_classes
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -447,3 +447,61 @@ def test_reading_from_a_pipe(mine, ref):
         snaps.append(snapshot(st.Structure(api, h)))
     assert snaps[0] == snaps[1]
     assert snaps[0] == snapshot(mine.from_pdb(text))
+
+
+@needs_ref
+def test_parallel_reader_is_identical_to_the_reference(mine, ref):
+    """Ranges of >= 1 MB are cut at safe line boundaries, parsed by several threads and stitched (ingest.c).  Forced on
+    for small inputs through the test hook; every thread count must reproduce the reference exactly, seams included."""
+    hook = mine.lib.fsb_ingest_parallel_reads
+    hook.restype = ctypes.c_long
+    texts = [w.pdb_text(900, seed=81, chains=4, models=1, hydrogens=0.3, hetatm=5, altloc=0.3, unknown=0.1).encode(),
+             w.pdb_text(700, seed=82, chains=2, models=3, hydrogens=0.1, altloc=0.2).encode(),
+             w.pdb_text(600, seed=83, chains=3, element_column=False, newline="\r\n").encode(),
+             EDGE_TEXTS["altloc_runs"].encode() * 40, EDGE_TEXTS["chain_returns"].encode() * 30,
+             (EDGE_TEXTS["insertion_codes"] * 25 + EDGE_TEXTS["coords_garbage"] + EDGE_TEXTS["insertion_codes"] * 25).encode(),
+             (EDGE_TEXTS["nucleic"] * 20 + EDGE_TEXTS["very_long_line"] + EDGE_TEXTS["nucleic"] * 20).encode()]
+    old = {k: os.environ.get(k) for k in ("FREESASA_B200_PARALLEL_MIN_BYTES", "FREESASA_B200_THREADS")}
+    try:
+        os.environ["FREESASA_B200_PARALLEL_MIN_BYTES"] = "1"
+        before = hook()
+        for threads in (2, 3, 7, 16):
+            os.environ["FREESASA_B200_THREADS"] = str(threads)
+            for text in texts:
+                for options in OPTION_SETS:
+                    same_structure(mine, ref, text, None, options)
+                for options in (st.SEPARATE_MODELS, st.SEPARATE_CHAINS | st.SEPARATE_MODELS):
+                    a, b = mine.array(text, None, options), ref.array(text, None, options)
+                    assert (a is None) == (b is None)
+                    if a is not None:
+                        assert [snapshot(x) for x in a] == [snapshot(x) for x in b]
+        assert hook() - before > 300  # the parallel path really ran
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_large_file_is_read_in_slices(mine, tmp_path):
+    """Files of >= 4 MB are read with pread() slices from several threads, then parsed in parallel: same structure as
+    the single-threaded reader gives for the same bytes."""
+    text = w.pdb_text(60000, seed=91, chains=5, hetatm=10).encode()
+    assert len(text) > (4 << 20)
+    path = os.path.join(tmp_path, "big.pdb")
+    with open(path, "wb") as f:
+        f.write(text)
+    old = os.environ.get("FREESASA_B200_THREADS")
+    try:
+        os.environ["FREESASA_B200_THREADS"] = "1"
+        serial = snapshot(mine.from_pdb(text))
+        os.environ["FREESASA_B200_THREADS"] = "6"
+        assert snapshot(mine.from_pdb_path(path)) == serial
+        assert snapshot(mine.from_pdb(text)) == serial
+    finally:
+        if old is None:
+            os.environ.pop("FREESASA_B200_THREADS", None)
+        else:
+            os.environ["FREESASA_B200_THREADS"] = old
+    assert serial["n"] == 60000 and serial["n_chains"] == 5
