@@ -558,6 +558,10 @@ fsb200_ctx *fsb200_ctx_create(int device)
     DeviceGuard guard(device);
     fsb200_ctx *c = new fsb200_ctx();
     c->device = device;
+    {   // FSB200_PRECISION=fp64: the drop-in entry points (which have no precision argument) use the all-fp64 kernels
+        const char *env = getenv("FSB200_PRECISION");
+        if (env && (strcmp(env, "fp64") == 0 || strcmp(env, "FP64") == 0 || strcmp(env, "double") == 0)) c->precision = FSB200_FP64;
+    }
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_status, sizeof(int) * kCtrCount) == cudaSuccess;

@@ -41,7 +41,9 @@ extern "C" {
 
 /* arithmetic of the integration kernels */
 #define FSB200_FP32 0 /* default: fp32 in the atom-local frame, fp64 neighbour test + fp64 tie re-check */
-#define FSB200_FP64 1 /* everything in fp64 (validation / maximum fidelity) */
+#define FSB200_FP64 1 /* everything in fp64 (validation / maximum fidelity); also selected for every new context by the
+                       * environment variable FSB200_PRECISION=fp64, which is how a caller of the drop-in entry points
+                       * (no precision argument) asks for it */
 
 typedef struct fsb200_ctx fsb200_ctx;
 

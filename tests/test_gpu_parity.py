@@ -386,3 +386,24 @@ def test_large_batch_overlapped_on_two_contexts_equals_one_pass(eng32):
     bad[100] = (np.full_like(structs[100][0], np.nan), structs[100][1])
     with pytest.raises(RuntimeError):
         fs.calc_coord_batch(bad, p)
+
+
+def test_precision_from_the_environment():
+    """FSB200_PRECISION=fp64 switches the drop-in entry points (no precision argument) to the all-fp64 kernels."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import numpy as np, freesasa_b200 as fs\n"
+            "from oracle import bindings as ob\n"
+            "x, r = fs.workloads.globule(4000, seed=12)\n"
+            "got = fs.calc_coord(x, r, fs.Parameters(fs.LEE_RICHARDS, 1.4, 100, 40, 1)).sasa\n"
+            "print(float(np.abs(got - ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, 40)).max()))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    errs = {}
+    for mode in ("fp64", "fp32"):
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, FSB200_PRECISION=mode, PYTHONPATH=root),
+                             check=True, capture_output=True, text=True).stdout
+        errs[mode] = float(out.strip().splitlines()[-1])
+    assert errs["fp64"] < LR_TOL_FP64
+    assert LR_TOL_FP64 < errs["fp32"] < LR_TOL_FP32

@@ -32,12 +32,13 @@ def timed(fn, reps, release=None):
     return best * 1e3, out
 
 
-def stages(api, text, params, reps):
-    """ms for read / calc / tree / tree free, and the per-atom result."""
+def stages(api, path, params, reps):
+    """ms for read (fopen + freesasa_structure_from_pdb on a file in /dev/shm) / calc / tree / tree free, and the
+    per-atom result."""
     L = api.lib
     L.freesasa_calc_structure.restype = ctypes.POINTER(api.Result)
     L.freesasa_tree_init.restype = ctypes.c_void_p
-    t_read, s = timed(lambda: api.from_pdb(text), reps, lambda x: x.free())
+    t_read, s = timed(lambda: api.from_pdb_path(path), reps, lambda x: x.free())
     t_calc, res = timed(lambda: L.freesasa_calc_structure(s.h, ctypes.byref(params)), reps, L.freesasa_result_free)
     if not res:
         raise RuntimeError("freesasa_calc_structure returned NULL")
@@ -58,22 +59,26 @@ def main():
     ref = st.StructureAPI(ob.ref_lib(), ob.RefResult, ob.RefParameters)
     for api in (mine, ref):
         api.lib.freesasa_set_verbosity(1)
-    out = {"host_threads_reference": threads, "cases": {}}
+    out = {"host_threads_reference": threads, "host_cpus": os.cpu_count(), "cases": {}}
     for name, n_atoms, chains in [("14k (2isk-sized)", 13928, 4), ("100k", 100000, 8)] + ([] if quick else [("1M", 1000000, 60)]):
         text = w.pdb_text(n_atoms, seed=5, chains=chains).encode()
+        path = "/dev/shm/_fsb_pipeline_%d.pdb" % n_atoms
+        with open(path, "wb") as f:
+            f.write(text)
         case = {"bytes": len(text)}
         for alg, res_n, key in [(fs.LEE_RICHARDS, 100, "LR-100"), (fs.LEE_RICHARDS, 20, "LR-20")]:
             reps = 3 if n_atoms <= 100000 else 1
-            m, sasa_m = stages(mine, text, fs.Parameters(alg, 1.4, res_n, res_n, 1), reps + 2)
+            m, sasa_m = stages(mine, path, fs.Parameters(alg, 1.4, res_n, res_n, 1), reps + 2)
             entry = {"this_repo": m}
             if n_atoms <= 100000 or key == "LR-20":
-                r, sasa_r = stages(ref, text, ob.RefParameters(alg, 1.4, res_n, res_n, threads), 1 if n_atoms > 20000 else reps)
+                r, sasa_r = stages(ref, path, ob.RefParameters(alg, 1.4, res_n, res_n, threads), 1 if n_atoms > 20000 else reps)
                 entry["reference"] = r
                 entry["max_abs_err"] = float(np.abs(sasa_m - sasa_r).max())
                 entry["speedup_total"] = r["total_ms"] / m["total_ms"]
             case[key] = entry
             print(name, key, json.dumps(entry), flush=True)
         out["cases"][name] = case
+        os.remove(path)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "pipeline.json"), "w") as f:
         json.dump(out, f, indent=1)
