@@ -19,7 +19,7 @@ LIB = os.path.join(CSRC, "libfsb200.so")
 SOURCES = ["api.cu", "cells.cu", "integrate.cu"]
 HEADERS = [os.path.join(CSRC, "engine.cuh"), os.path.join(CSRC, "cert_dirs.inc"), os.path.join(ROOT, "include", "fsb200.h")]
 HOST_LIB = os.path.join(CSRC, "libfreesasa_b200_host.so")
-HOST_SOURCES = ["host_shim.c", "radii.c", "ingest.c", "areas.c", "workers.c"]
+HOST_SOURCES = ["host_shim.c", "radii.c", "ingest.c", "areas.c", "select.c", "workers.c"]
 HOST_HEADERS = [os.path.join(ROOT, "include", "freesasa_b200_host.h"), os.path.join(ROOT, "include", "fsb200.h"),
                 os.path.join(CSRC, "host_internal.h"), os.path.join(CSRC, "radius_tables.inc")]
 

@@ -50,6 +50,7 @@ struct freesasa_node {
             int n_chains, n_atoms, model;
             const char *chain_labels;
             freesasa_result *result;
+            freesasa_selection **selection; /* NULL-terminated array of clones, or NULL (src/node.c:32-40) */
         } structure;
         struct {
             const char *classified_by;
@@ -146,6 +147,12 @@ freesasa_node *freesasa_tree_new(void)
 static void block_free(freesasa_node *result_node)
 {
     struct tree_block *b = result_node->p.result.block;
+    freesasa_selection **sel = result_node->children->p.structure.selection;
+    if (sel) {
+        freesasa_selection **it;
+        for (it = sel; *it; ++it) freesasa_selection_free(*it);
+        free(sel);
+    }
     fsb_text_release(b->text);
     free(b->lines);
     free(b); /* nodes, areas, strings and the cloned result all live in this allocation */
@@ -578,6 +585,28 @@ const freesasa_result *freesasa_node_structure_result(const freesasa_node *node)
 {
     assert(node->type == FREESASA_NODE_STRUCTURE);
     return node->p.structure.result;
+}
+/* src/node.c:670-709: the node keeps its own copy of every selection added */
+int freesasa_node_structure_add_selection(freesasa_node *node, const freesasa_selection *selection)
+{
+    freesasa_selection **sel;
+    int n = 0;
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    sel = node->p.structure.selection;
+    if (sel)
+        while (sel[n]) ++n;
+    sel = realloc(sel, sizeof(freesasa_selection *) * (size_t)(n + 2));
+    if (sel == NULL) return MEM_FAIL();
+    node->p.structure.selection = sel;
+    sel[n] = freesasa_selection_clone(selection);
+    sel[n + 1] = NULL;
+    if (sel[n] == NULL) return FAIL_MSG("%s", "");
+    return FREESASA_SUCCESS;
+}
+const freesasa_selection **freesasa_node_structure_selections(const freesasa_node *node)
+{
+    assert(node->type == FREESASA_NODE_STRUCTURE);
+    return (const freesasa_selection **)node->p.structure.selection;
 }
 const freesasa_parameters *freesasa_node_result_parameters(const freesasa_node *node)
 {

@@ -93,6 +93,7 @@ struct freesasa_nodearea {
 
 typedef struct freesasa_classifier freesasa_classifier; /* opaque, src/freesasa.h:345 */
 typedef struct freesasa_structure freesasa_structure;   /* opaque, src/freesasa.h:353 */
+typedef struct freesasa_selection freesasa_selection;   /* opaque, src/freesasa.h:369 */
 #ifndef __cplusplus
 typedef enum freesasa_atom_class freesasa_atom_class;
 typedef struct freesasa_nodearea freesasa_nodearea;
@@ -215,6 +216,20 @@ int freesasa_node_structure_model(const freesasa_node *node);
 const char *freesasa_node_structure_chain_labels(const freesasa_node *node);
 const freesasa_result *freesasa_node_structure_result(const freesasa_node *node);
 const freesasa_parameters *freesasa_node_result_parameters(const freesasa_node *node);
+int freesasa_node_structure_add_selection(freesasa_node *node, const freesasa_selection *selection);
+const freesasa_selection **freesasa_node_structure_selections(const freesasa_node *node);
+/* row f-4, selections: reference src/freesasa.h:610-690,1855-1882, src/selection.c.  The command language is the
+ * reference's ("name, resn ala+arg and not chain A", "s, resi 10-20+\-3", ...; doc/doxy-main.md "Selection syntax"). */
+freesasa_selection *freesasa_selection_new(const char *command, const freesasa_structure *structure, const freesasa_result *result);
+void freesasa_selection_free(freesasa_selection *selection);
+freesasa_selection *freesasa_selection_clone(const freesasa_selection *selection);
+const char *freesasa_selection_name(const freesasa_selection *selection);
+const char *freesasa_selection_command(const freesasa_selection *selection);
+double freesasa_selection_area(const freesasa_selection *selection);
+int freesasa_selection_n_atoms(const freesasa_selection *selection);
+int freesasa_select_area(const char *command, char *name, double *area, const freesasa_structure *structure,
+                         const freesasa_result *result);
+#define FREESASA_MAX_SELECTION_NAME 50
 /* row f-4, per-atom writer: reference src/freesasa_internal.h:200, src/pdb.c:347-375 (what the CLI's --format=pdb and
  * freesasa_tree_export(..., FREESASA_PDB) emit) */
 int freesasa_write_pdb(FILE *output, freesasa_node *root);

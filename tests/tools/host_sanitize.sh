@@ -9,16 +9,16 @@ CSRC=$ROOT/freesasa_b200/csrc
 CC=/usr/bin/gcc
 ASAN=$($CC -print-file-name=libasan.so)
 TMP=$(mktemp -d)
-SRC="$CSRC/host_shim.c $CSRC/radii.c $CSRC/ingest.c $CSRC/areas.c $CSRC/workers.c"
+SRC="$CSRC/host_shim.c $CSRC/radii.c $CSRC/ingest.c $CSRC/areas.c $CSRC/select.c $CSRC/workers.c"
 $CC -std=gnu99 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fPIC -shared -I "$ROOT/include" \
     -o "$TMP/libfreesasa_b200_host.so" $SRC -L "$CSRC" -lfsb200 -Wl,-rpath,"$CSRC" -lm -lpthread
 cp "$CSRC/libfreesasa_b200_host.so" "$TMP/plain.so"
 trap 'cp "$TMP/plain.so" "$CSRC/libfreesasa_b200_host.so"; touch "$CSRC/libfreesasa_b200_host.so"; rm -rf "$TMP"' EXIT
 cp "$TMP/libfreesasa_b200_host.so" "$CSRC/libfreesasa_b200_host.so"; touch "$CSRC/libfreesasa_b200_host.so"
 cd "$ROOT"
-LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python -m pytest tests/test_ingest.py tests/test_areas.py -x -q -p no:cacheprovider
+LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python -m pytest tests/test_ingest.py tests/test_areas.py tests/test_select.py -x -q -p no:cacheprovider
 LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 FREESASA_B200_PARALLEL_MIN_BYTES=1 FREESASA_B200_PARALLEL_MIN_ATOMS=1 \
-    FREESASA_B200_THREADS=4 python -m pytest tests/test_ingest.py tests/test_areas.py -x -q -p no:cacheprovider
+    FREESASA_B200_THREADS=4 python -m pytest tests/test_ingest.py tests/test_areas.py tests/test_select.py -x -q -p no:cacheprovider
 # leak check: the engine entry points are stubbed (no GPU needed; nothing here computes SASA)
 printf 'const char *fsb200_last_error(void){return "";}\nint fsb200_lr(){return -1;}\nint fsb200_sr(){return -1;}\nint fsb200_calc_batch(){return -1;}\n' > "$TMP/stub.c"
 $CC -std=gnu99 -O1 -g -fsanitize=address,undefined -I "$ROOT/include" "$ROOT/tests/tools/host_leakcheck.c" $SRC "$TMP/stub.c" -o "$TMP/leak" -lm -lpthread
