@@ -13,6 +13,9 @@ int main(int argc,char**argv){
       if(s){ int n=freesasa_structure_n(s); freesasa_result r; r.n_atoms=n; r.sasa=malloc(8*n); for(int i=0;i<n;i++) r.sasa[i]=i%7; r.total=1; r.parameters=freesasa_default_parameters;
         freesasa_node*t=freesasa_tree_init(&r,s,"x"); freesasa_node *t2=freesasa_tree_init(&r,s,NULL); freesasa_tree_join(t,&t2);
         FILE*o=fopen("/dev/null","w"); freesasa_write_pdb(o,t); fclose(o);
+        { const char *cmds[] = {"a, resn ALA+GLY and not chain B", "b, resi 1-20+\\-3 or name CA", "c, resn ALAA", "d resn", "e, resn ALA and"};
+          for (int q=0;q<5;q++){ freesasa_selection *sel=freesasa_selection_new(cmds[q],s,&r); if(sel){ freesasa_selection *cl=freesasa_selection_clone(sel);
+            freesasa_node_structure_add_selection(freesasa_node_children(freesasa_node_children(t)), sel); freesasa_selection_free(cl); freesasa_selection_free(sel);} } }
         freesasa_structure*c=freesasa_structure_get_chains(s,"A",NULL,0); freesasa_structure_free(c);
         (void)freesasa_structure_atom_pdb_line(s,0);
         freesasa_node_free(t); free(r.sasa); freesasa_structure_free(s);} 
