@@ -903,14 +903,14 @@ serial:
 }
 
 /* from_pdb_impl(), src/structure.c:638-721, on the byte range [begin, end] of the text */
-static freesasa_structure *from_range(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
-                                      int options)
+static freesasa_structure *from_range_opt(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
+                                          int options, int allow_threads)
 {
     freesasa_structure *s = NULL;
     struct memo *memo;
     struct scan_info info = {0, 0, 0, 0};
 
-    if (from_range_parallel(t, begin, end, classifier, options, &s)) return s;
+    if (allow_threads && from_range_parallel(t, begin, end, classifier, options, &s)) return s;
     s = fragment_new(t, (end < t->len ? end : t->len) - begin);
     memo = calloc(1, sizeof *memo);
     if (s == NULL || memo == NULL) {
@@ -931,6 +931,12 @@ fail:
     free(memo);
     freesasa_structure_free(s);
     return NULL;
+}
+
+static freesasa_structure *from_range(const struct shared_text *t, long begin, long end, const freesasa_classifier *classifier,
+                                      int options)
+{
+    return from_range_opt(t, begin, end, classifier, options, 1);
 }
 
 freesasa_structure *freesasa_structure_from_pdb(FILE *pdb_file, const freesasa_classifier *classifier, int options)
@@ -1053,12 +1059,47 @@ static int find_chains(const struct shared_text *t, struct range model, struct r
     return n;
 }
 
+/* One structure-to-be of freesasa_structure_array(): a byte range and the model number it gets, or (range.begin < 0) just
+ * a message that the serial reader would have printed at this point. */
+struct piece {
+    struct range range;
+    int model;
+    freesasa_structure *structure;
+    struct fsb_capture messages;
+};
+struct piece_work {
+    const struct shared_text *t;
+    const freesasa_classifier *classifier;
+    int options, n_pieces, next;
+    struct piece *pieces;
+};
+static void piece_worker(int part, int n_parts, void *arg)
+{
+    struct piece_work *w = arg;
+    (void)part;
+    (void)n_parts;
+    for (;;) {
+        const int k = __atomic_fetch_add(&w->next, 1, __ATOMIC_RELAXED);
+        struct piece *p;
+        if (k >= w->n_pieces) break;
+        p = &w->pieces[k];
+        if (p->range.begin < 0) continue;
+        fsb_capture_current = &p->messages;
+        p->structure = from_range_opt(w->t, p->range.begin, p->range.end, w->classifier, w->options, 0);
+        fsb_capture_current = NULL;
+    }
+}
+
+/* freesasa_structure_array(), src/structure.c:848-953.  The ranges (models, chains) are found first; with many of them
+ * (an NMR ensemble, the chains of a large assembly) they are parsed concurrently, each with its messages captured, and
+ * the outcome — structures, messages, the point of failure — is replayed in file order, i.e. exactly the serial one. */
 freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_classifier *classifier, int options)
 {
     struct shared_text *t;
     struct range *models = NULL, *chains = NULL, whole;
+    struct piece *pieces = NULL;
     freesasa_structure **ss = NULL;
-    int n_models, n_total = 0, i, j;
+    int n_models, n_pieces = 0, cap_pieces = 0, n_total = 0, i, j, failed = 0, threads;
 
     assert(pdb);
     assert(n);
@@ -1082,56 +1123,90 @@ freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_
     }
     if (!(options & FREESASA_SEPARATE_MODELS)) n_models = 1; /* only the first model */
 
-    if (options & FREESASA_SEPARATE_CHAINS) {
-        for (i = 0; i < n_models; ++i) {
-            void *p;
-            const int n_new = find_chains(t, models[i], &chains, options);
-            if (n_new == FREESASA_FAIL) goto fail;
-            if (n_new == 0) {
-                WARN_MSG("in %s(): no chains found (in model %d)", __func__, i + 1);
-                continue;
+    /* the pieces, in file order */
+    for (i = 0; i < n_models && !failed; ++i) {
+        int n_new = 1;
+        if (options & FREESASA_SEPARATE_CHAINS) {
+            n_new = find_chains(t, models[i], &chains, options);
+            if (n_new == FREESASA_FAIL) {
+                failed = 1;
+                break;
             }
-            if (!(p = realloc(ss, sizeof(freesasa_structure *) * (size_t)(n_total + n_new)))) {
+        }
+        if (n_pieces + (n_new > 0 ? n_new : 1) > cap_pieces) {
+            void *p = realloc(pieces, sizeof(struct piece) * (size_t)(cap_pieces = 2 * cap_pieces + n_new + 16));
+            if (!p) {
                 MEM_FAIL();
-                goto fail;
+                failed = 1;
+                break;
             }
-            ss = p;
-            for (j = 0; j < n_new; ++j) ss[n_total + j] = NULL;
-            n_total += n_new;
-            for (j = 0; j < n_new; ++j) {
-                ss[n_total - n_new + j] = from_range(t, chains[j].begin, chains[j].end, classifier, options);
-                if (ss[n_total - n_new + j] == NULL) goto fail;
-                ss[n_total - n_new + j]->model = i + 1;
-            }
-            free(chains);
-            chains = NULL;
+            pieces = p;
         }
-    } else {
-        if (!(ss = calloc((size_t)n_models, sizeof(freesasa_structure *)))) {
-            MEM_FAIL();
-            goto fail;
+        if (n_new == 0) { /* a model without atoms: the reference warns and goes on */
+            struct piece *p = &pieces[n_pieces++];
+            memset(p, 0, sizeof *p);
+            p->range.begin = -1;
+            fsb_capture_current = &p->messages;
+            WARN_MSG("in %s(): no chains found (in model %d)", __func__, i + 1);
+            fsb_capture_current = NULL;
+            continue;
         }
-        n_total = n_models;
-        for (i = 0; i < n_models; ++i) {
-            ss[i] = from_range(t, models[i].begin, models[i].end, classifier, options);
-            if (ss[i] == NULL) goto fail;
-            ss[i]->model = i + 1;
+        for (j = 0; j < n_new; ++j) {
+            struct piece *p = &pieces[n_pieces++];
+            memset(p, 0, sizeof *p);
+            p->range = (options & FREESASA_SEPARATE_CHAINS) ? chains[j] : models[i];
+            p->model = i + 1;
+        }
+        free(chains);
+        chains = NULL;
+    }
+
+    /* parse: concurrently when there are enough pieces to go round, else one after the other (where a large piece may
+     * itself be read in parallel); stop at the first failure either way */
+    threads = fsb_hardware_threads();
+    if (!failed && n_pieces >= 4 && threads >= 2) {
+        struct piece_work w = {t, classifier, options, n_pieces, 0, pieces};
+        fsb_parallel_run(threads < n_pieces ? threads : n_pieces, piece_worker, &w);
+    } else if (!failed) {
+        for (i = 0; i < n_pieces; ++i) {
+            fsb_capture_flush(&pieces[i].messages); /* a "no chains found" warning, at its place in the sequence */
+            if (pieces[i].range.begin < 0) continue;
+            pieces[i].structure = from_range(t, pieces[i].range.begin, pieces[i].range.end, classifier, options);
+            if (pieces[i].structure == NULL) break; /* later pieces are never read */
         }
     }
-    if (n_total == 0) goto fail;
+    /* replay in file order */
+    if (!failed && n_pieces > 0 && !(ss = calloc((size_t)n_pieces, sizeof(freesasa_structure *)))) {
+        MEM_FAIL();
+        failed = 1;
+    }
+    for (i = 0; i < n_pieces && !failed; ++i) {
+        fsb_capture_flush(&pieces[i].messages);
+        if (pieces[i].range.begin < 0) continue;
+        if (pieces[i].structure == NULL) {
+            failed = 1;
+            break;
+        }
+        pieces[i].structure->model = pieces[i].model;
+        ss[n_total++] = pieces[i].structure;
+        pieces[i].structure = NULL;
+    }
+    if (n_total == 0) failed = 1;
+    for (i = 0; i < n_pieces; ++i) { /* whatever was not handed over */
+        free(pieces[i].messages.text);
+        freesasa_structure_free(pieces[i].structure);
+    }
+    free(pieces);
+    free(chains);
     if (models != &whole) free(models);
     fsb_text_release(t);
+    if (failed) {
+        for (i = 0; i < n_total; ++i) freesasa_structure_free(ss[i]);
+        free(ss);
+        return NULL;
+    }
     *n = n_total;
     return ss;
-fail:
-    if (ss)
-        for (i = 0; i < n_total; ++i) freesasa_structure_free(ss[i]);
-    if (models != &whole) free(models);
-    free(chains);
-    free(ss);
-    fsb_text_release(t);
-    *n = 0;
-    return NULL;
 }
 
 /* freesasa_structure_get_chains(), src/structure.c:955-1010 */

@@ -150,6 +150,17 @@ class StructureAPI:
         _libc.free(ctypes.cast(arr, _vp))
         return out
 
+    def array_path(self, path: str, classifier=None, options: int = SEPARATE_MODELS):
+        """freesasa_structure_array() on a file."""
+        n = ctypes.c_int(0)
+        with CFile(path=path) as fp:
+            arr = self.lib.freesasa_structure_array(fp, ctypes.byref(n), classifier, options)
+        if not arr:
+            return None
+        out = [Structure(self, arr[k]) for k in range(n.value)]
+        _libc.free(ctypes.cast(arr, _vp))
+        return out
+
     def new(self):
         return Structure(self, self.lib.freesasa_structure_new())
 
