@@ -248,7 +248,8 @@ static void build_part(int part, int n_parts, void *arg)
  * (src/node.c:214-409) fused: a serial pass over the chains, one pass over residues and atoms (split over threads for
  * large structures: every string lives at an index-derived place in the pool, so the parts are independent), then the
  * chain and structure sums in order */
-int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *s, const char *name)
+static int tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *s, const char *name,
+                           int allow_threads)
 {
     const int n = s->n, n_res = s->n_res, n_chains = s->n_chains;
     const size_t n_nodes = 2 + (size_t)n_chains + (size_t)n_res + (size_t)n;
@@ -367,7 +368,7 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
         /* FREESASA_B200_PARALLEL_MIN_ATOMS: test hook, lets the test-suite drive small structures through the threaded build */
         const char *env = getenv("FREESASA_B200_PARALLEL_MIN_ATOMS");
         const int min_atoms = env ? atoi(env) : 20000, per_part = min_atoms / 2 > 16 ? min_atoms / 2 : 16;
-        parts = n >= min_atoms ? fsb_hardware_threads() : 1;
+        parts = allow_threads && n >= min_atoms ? fsb_hardware_threads() : 1;
         if (parts > n / per_part) parts = n / per_part > 0 ? n / per_part : 1;
     }
     if (parts > 1)
@@ -389,6 +390,11 @@ int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result,
     rnode->next = tree->children;
     tree->children = rnode;
     return FREESASA_SUCCESS;
+}
+
+int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *s, const char *name)
+{
+    return tree_add_result(tree, result, s, name, 1);
 }
 
 freesasa_node *freesasa_tree_init(const freesasa_result *result, const freesasa_structure *structure, const char *name)
@@ -459,6 +465,86 @@ freesasa_node *freesasa_calc_tree(const freesasa_structure *structure, const fre
     if (tree == NULL) FAIL_MSG("%s", "");
     freesasa_result_free(result);
     return tree;
+}
+
+/* Additive (row f-2): what the CLI's loop over structures (src/main.cc:334-362: freesasa_calc_tree per model / chain
+ * group) becomes with a batched engine — every structure of an array in ONE device pass, then one tree per structure, the
+ * trees built concurrently on the host's cores.  trees[k] receives a tree as freesasa_calc_tree(structures[k], parameters,
+ * names ? names[k] : NULL) would return it; on failure no tree is left allocated.  Messages come out in structure order. */
+struct tree_batch {
+    int n, next;
+    freesasa_structure *const *structures;
+    freesasa_result **results;
+    const char *const *names;
+    freesasa_node **trees;
+    struct fsb_capture *messages;
+};
+static void tree_batch_worker(int part, int n_parts, void *arg)
+{
+    struct tree_batch *w = arg;
+    (void)part;
+    (void)n_parts;
+    for (;;) {
+        const int k = __atomic_fetch_add(&w->next, 1, __ATOMIC_RELAXED);
+        freesasa_node *tree;
+        if (k >= w->n) break;
+        fsb_capture_current = &w->messages[k];
+        tree = freesasa_tree_new();
+        if (tree && tree_add_result(tree, w->results[k], w->structures[k], w->names ? w->names[k] : NULL, 0) == FREESASA_FAIL) {
+            freesasa_node_free(tree);
+            tree = NULL;
+        }
+        w->trees[k] = tree;
+        fsb_capture_current = NULL;
+    }
+}
+/* One tree per (structure, result) pair, built concurrently; messages replayed in order.  On failure no tree is left. */
+int fsb_trees_from_results(int n_struct, freesasa_structure *const *structures, freesasa_result *const *results,
+                           const char *const *names, freesasa_node **trees)
+{
+    struct tree_batch w;
+    int k, failed = 0, threads;
+    for (k = 0; k < n_struct; ++k) trees[k] = NULL;
+    memset(&w, 0, sizeof w);
+    w.n = n_struct;
+    w.structures = structures;
+    w.results = (freesasa_result **)results;
+    w.names = names;
+    w.trees = trees;
+    if (!(w.messages = calloc((size_t)n_struct, sizeof *w.messages))) return MEM_FAIL();
+    threads = fsb_hardware_threads();
+    fsb_parallel_run(threads < n_struct ? threads : n_struct, tree_batch_worker, &w);
+    for (k = 0; k < n_struct; ++k) {
+        fsb_capture_flush(&w.messages[k]);
+        if (trees[k] == NULL) failed = 1;
+    }
+    free(w.messages);
+    if (failed) {
+        for (k = 0; k < n_struct; ++k) {
+            freesasa_node_free(trees[k]);
+            trees[k] = NULL;
+        }
+        return FAIL_MSG("%s", "");
+    }
+    return FREESASA_SUCCESS;
+}
+
+int freesasa_calc_tree_batch(int n_struct, freesasa_structure *const *structures, const freesasa_parameters *parameters,
+                             const char *const *names, freesasa_node **trees)
+{
+    freesasa_result **results;
+    int k, rc;
+    if (n_struct <= 0 || !structures || !trees) return FAIL_MSG("invalid batch arguments");
+    for (k = 0; k < n_struct; ++k) trees[k] = NULL;
+    if (!(results = calloc((size_t)n_struct, sizeof *results))) return MEM_FAIL();
+    if (freesasa_calc_structure_batch(n_struct, structures, parameters, results) != FREESASA_SUCCESS) {
+        free(results);
+        return FAIL_MSG("%s", "");
+    }
+    rc = fsb_trees_from_results(n_struct, structures, results, names, trees);
+    for (k = 0; k < n_struct; ++k) freesasa_result_free(results[k]);
+    free(results);
+    return rc;
 }
 
 /* ---- accessors (src/node.c:515-716) ----------------------------------------------------------------------- */

@@ -185,6 +185,10 @@ extern const freesasa_nodearea freesasa_nodearea_null; /* src/freesasa_internal.
 /* reference src/freesasa.h:497-519,1460-1549 */
 freesasa_node *freesasa_calc_tree(const freesasa_structure *structure, const freesasa_parameters *parameters, const char *name);
 freesasa_nodearea freesasa_result_classes(const freesasa_structure *structure, const freesasa_result *result);
+/* Additive (row f-2): all structures in ONE device pass, then one tree each (built concurrently); trees[k] is what
+ * freesasa_calc_tree(structures[k], parameters, names ? names[k] : NULL) returns.  FREESASA_SUCCESS or FREESASA_FAIL. */
+int freesasa_calc_tree_batch(int n_struct, freesasa_structure *const *structures, const freesasa_parameters *parameters,
+                             const char *const *names, freesasa_node **trees);
 freesasa_node *freesasa_tree_new(void);
 freesasa_node *freesasa_tree_init(const freesasa_result *result, const freesasa_structure *structure, const char *name);
 int freesasa_tree_add_result(freesasa_node *tree, const freesasa_result *result, const freesasa_structure *structure,

@@ -196,3 +196,49 @@ def test_threaded_tree_build_is_identical(both):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+@needs_ref
+def test_trees_of_a_batch_built_concurrently(both):
+    """The tree half of the additive freesasa_calc_tree_batch(): many (structure, result) pairs -> trees on several threads;
+    each equals the reference's freesasa_tree_init() of the same pair.  Without a GPU the full call must fail loudly."""
+    import os
+
+    import freesasa_b200 as fs
+
+    (mine, tm), (ref, tr) = both
+    text = w.pdb_text(700, seed=41, chains=2, models=7, hetatm=2).encode()
+    sm, sr = mine.array(text, None, st.SEPARATE_MODELS), ref.array(text, None, st.SEPARATE_MODELS)
+    n = len(sm)
+    rng = np.random.default_rng(8)
+    sasa = [rng.uniform(0, 50, size=s.n) for s in sm]
+    res_m = [tm.make_result(a) for a in sasa]
+    res_r = [tr.make_result(a) for a in sasa]
+    H = mine.lib
+    H.fsb_trees_from_results.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.POINTER(mine.Result)),
+                                         ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_void_p)]
+    handles = (ctypes.c_void_p * n)(*[s.h for s in sm])
+    results = (ctypes.POINTER(mine.Result) * n)(*[ctypes.pointer(r[0]) for r in res_m])
+    names = (ctypes.c_char_p * n)(*[b"m%d" % k for k in range(n)])
+    trees = (ctypes.c_void_p * n)()
+    old = os.environ.get("FREESASA_B200_THREADS")
+    try:
+        for threads in ("1", "3", "16"):
+            os.environ["FREESASA_B200_THREADS"] = threads
+            assert H.fsb_trees_from_results(n, handles, results, names, trees) == 0
+            for k in range(n):
+                want = tr.init(res_r[k][0], sr[k], b"m%d" % k)
+                assert tm.walk(trees[k]) == tr.walk(want)
+                tr.free(want)
+                tm.free(trees[k])
+    finally:
+        if old is None:
+            os.environ.pop("FREESASA_B200_THREADS", None)
+        else:
+            os.environ["FREESASA_B200_THREADS"] = old
+    if not fs.available():
+        H.freesasa_calc_tree_batch.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(fs.Parameters),
+                                               ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_void_p)]
+        p = fs.default_parameters()
+        assert H.freesasa_calc_tree_batch(n, handles, ctypes.byref(p), names, trees) == -1
+        assert not any(trees[k] for k in range(n))

@@ -98,3 +98,28 @@ def test_structure_array_as_one_batch(mine, ref, options):
         assert np.array_equal(got, single)
         assert float(np.abs(got - want).max()) <= SR_TOL
         H.freesasa_result_free(results[k])
+
+
+def test_calc_tree_batch_equals_one_tree_per_structure(mine):
+    """Additive freesasa_calc_tree_batch(): one device pass + trees built concurrently == freesasa_calc_tree() per structure."""
+    text = w.pdb_text(1200, seed=6, chains=3, models=9, hetatm=2).encode()
+    structures = mine.array(text, None, st.SEPARATE_MODELS | st.INCLUDE_HETATM)
+    n = len(structures)
+    assert n == 9
+    H, tree = mine.lib, st.TreeAPI(mine)
+    H.freesasa_calc_tree_batch.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(fs.Parameters),
+                                           ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_void_p)]
+    p = fs.Parameters(fs.SHRAKE_RUPLEY, 1.4, 150, 20, 1)
+    handles = (ctypes.c_void_p * n)(*[s.h for s in structures])
+    names = (ctypes.c_char_p * n)(*[b"model-%d" % k for k in range(n)])
+    trees = (ctypes.c_void_p * n)()
+    assert H.freesasa_calc_tree_batch(n, handles, ctypes.byref(p), names, trees) == 0
+    for k in range(n):
+        single = H.freesasa_calc_tree(structures[k].h, ctypes.byref(p), names[k])
+        assert tree.walk(trees[k]) == tree.walk(single)
+        tree.free(single)
+        tree.free(trees[k])
+    assert H.freesasa_calc_tree_batch(n, handles, ctypes.byref(p), None, trees) == 0  # names are optional
+    assert tree.walk(trees[0])[1][2] is None
+    for k in range(n):
+        tree.free(trees[k])

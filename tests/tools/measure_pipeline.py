@@ -52,7 +52,7 @@ def stages(api, path, params, reps):
             "total_ms": t_read + t_calc + t_tree}, sasa
 
 
-def ensemble_side(api, path, params, batch, reps):
+def ensemble_side(api, path, params, batch, reps, tree_batch=False):
     """read (freesasa_structure_array) / calc / one tree per model, best of `reps`; `batch`: all models in one
     freesasa_calc_structure_batch() call (this repo), else one freesasa_calc_structure() per model (the CLI's loop)."""
     L = api.lib
@@ -70,6 +70,22 @@ def ensemble_side(api, path, params, batch, reps):
         t1 = time.perf_counter()
         n = len(structures)
         results = (res_p * n)()
+        if tree_batch:  # calculation and trees in one call (additive freesasa_calc_tree_batch)
+            L.freesasa_calc_tree_batch.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(api.Parameters),
+                                                   ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_void_p)]
+            handles = (ctypes.c_void_p * n)(*[s.h for s in structures])
+            tree_arr = (ctypes.c_void_p * n)()
+            assert L.freesasa_calc_tree_batch(n, handles, ctypes.byref(params), None, tree_arr) == 0
+            t3 = t2 = time.perf_counter()
+            totals = [L.freesasa_node_area(L.freesasa_node_children(L.freesasa_node_children(tree_arr[k]))).contents.total for k in range(n)]
+            for k in range(n):
+                L.freesasa_node_free(tree_arr[k])
+            for s in structures:
+                s.free()
+            best["read_ms"] = min(best["read_ms"], (t1 - t0) * 1e3)
+            best["calc_ms"] = min(best["calc_ms"], (t2 - t1) * 1e3)
+            best["tree_ms"] = 0.0
+            continue
         if batch:
             handles = (ctypes.c_void_p * n)(*[s.h for s in structures])
             assert L.freesasa_calc_structure_batch(n, handles, ctypes.byref(params), results) == 0
@@ -101,9 +117,14 @@ def ensemble(mine, ref, threads, n_models=64, n_atoms=5000):
         f.write(text)
     out = {"models": n_models, "bytes": len(text)}
     out["this_repo"], totals = ensemble_side(mine, path, fs.Parameters(fs.LEE_RICHARDS, 1.4, 100, 20, 1), True, 4)
+    fused, totals_f = ensemble_side(mine, path, fs.Parameters(fs.LEE_RICHARDS, 1.4, 100, 20, 1), True, 4, tree_batch=True)
+    fused["note"] = "calc_ms = freesasa_calc_tree_batch(): device pass + all trees"
+    out["this_repo_tree_batch"] = fused
+    assert totals_f == totals
     out["reference"], ref_totals = ensemble_side(ref, path, ob.RefParameters(fs.LEE_RICHARDS, 1.4, 100, 20, threads), False, 1)
     out["max_abs_err_total"] = float(max(abs(a - b) for a, b in zip(totals, ref_totals)))
     out["speedup_total"] = out["reference"]["total_ms"] / out["this_repo"]["total_ms"]
+    out["speedup_total_tree_batch"] = out["reference"]["total_ms"] / fused["total_ms"]
     os.remove(path)
     return out
 
