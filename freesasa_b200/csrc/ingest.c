@@ -291,6 +291,33 @@ int freesasa_structure_add_atom(freesasa_structure *structure, const char *atom_
     return add_atom_wopt(structure, atom_name, residue_name, residue_number, NULL, label, x, y, z, NULL, 0);
 }
 
+/* freesasa_structure_add_cif_atom() / _lcl(), src/structure.c:793-829: what an mmCIF reader (the reference's is the
+ * gemmi-based src/cif.cc, outside this library) calls per _atom_site row */
+static int add_cif_atom(freesasa_structure *structure, const char *atom_id, const char *comp_id, const char *seq_id,
+                        const char *ins_code, const char *symbol, const char *chain, double x, double y, double z,
+                        const freesasa_classifier *classifier, int options)
+{
+    char res_number[6];
+    if (ins_code[0] != '?')
+        snprintf(res_number, sizeof res_number, "%s%c", seq_id, ins_code[0]);
+    else
+        snprintf(res_number, sizeof res_number, "%s", seq_id);
+    return add_atom_wopt(structure, atom_id, comp_id, res_number, symbol, chain, x, y, z, classifier, options);
+}
+int freesasa_structure_add_cif_atom(freesasa_structure *structure, freesasa_cif_atom *atom, const freesasa_classifier *classifier,
+                                    int options)
+{
+    const char label[2] = {atom->auth_asym_id, '\0'};
+    return add_cif_atom(structure, atom->auth_atom_id, atom->auth_comp_id, atom->auth_seq_id, atom->pdbx_PDB_ins_code,
+                        atom->type_symbol, label, atom->Cartn_x, atom->Cartn_y, atom->Cartn_z, classifier, options);
+}
+int freesasa_structure_add_cif_atom_lcl(freesasa_structure *structure, freesasa_cif_atom_lcl *atom,
+                                        const freesasa_classifier *classifier, int options)
+{
+    return add_cif_atom(structure, atom->auth_atom_id, atom->auth_comp_id, atom->auth_seq_id, atom->pdbx_PDB_ins_code,
+                        atom->type_symbol, atom->auth_asym_id, atom->Cartn_x, atom->Cartn_y, atom->Cartn_z, classifier, options);
+}
+
 /* ---- PDB text ---------------------------------------------------------------------------------------- */
 /* Large regular files are read in slices by several threads (pread: the copy out of the page cache and the first touch
  * of the destination pages are the cost, and both parallelise).  Returns the bytes read or -1 to ask for a plain fread. */
@@ -1209,19 +1236,24 @@ freesasa_structure **freesasa_structure_array(FILE *pdb, int *n, const freesasa_
     return ss;
 }
 
-/* freesasa_structure_get_chains(), src/structure.c:955-1010 */
-freesasa_structure *freesasa_structure_get_chains(const freesasa_structure *structure, const char *chains,
-                                                  const freesasa_classifier *classifier, int options)
+/* freesasa_structure_get_chains() / _lcl(), src/structure.c:955-1081 */
+static int in_group(const freesasa_chain_group *group, const char *chain)
+{
+    size_t k;
+    for (k = 0; k < group->n; ++k)
+        if (strncmp(group->chains[k], chain, 4) == 0) return 1;
+    return 0;
+}
+static freesasa_structure *get_chains(const freesasa_structure *structure, const char *chains, const freesasa_chain_group *group,
+                                      const freesasa_classifier *classifier, int options)
 {
     freesasa_structure *out;
     int i;
-    assert(structure);
-    if (strlen(chains) == 0) return NULL;
     if (!(out = freesasa_structure_new())) return NULL;
     out->model = structure->model;
     for (i = 0; i < structure->n; ++i) {
         const struct atom_label *a = &structure->label[i];
-        if (strchr(chains, a->chain[0]) != NULL) {
+        if (group ? in_group(group, a->chain) : strchr(chains, a->chain[0]) != NULL) {
             const double *v = structure->coord.xyz + 3 * i;
             if (add_atom_wopt(out, a->name, a->res_name, a->res_number, a->symbol, a->chain, v[0], v[1], v[2], classifier,
                               options) == FREESASA_FAIL) {
@@ -1231,14 +1263,29 @@ freesasa_structure *freesasa_structure_get_chains(const freesasa_structure *stru
         }
     }
     if (out->n == 0) goto fail;
-    if ((size_t)out->n_chains != strlen(chains)) {
-        FAIL_MSG("structure has chains '%s', but '%s' requested", structure->short_labels, chains);
+    if ((size_t)out->n_chains != (group ? group->n : strlen(chains))) {
+        FAIL_MSG("structure has chains '%s', but '%s' requested", structure->short_labels, group ? "(chain group)" : chains);
         goto fail;
     }
     return out;
 fail:
     freesasa_structure_free(out);
     return NULL;
+}
+freesasa_structure *freesasa_structure_get_chains(const freesasa_structure *structure, const char *chains,
+                                                  const freesasa_classifier *classifier, int options)
+{
+    assert(structure);
+    if (strlen(chains) == 0) return NULL;
+    return get_chains(structure, chains, NULL, classifier, options);
+}
+freesasa_structure *freesasa_structure_get_chains_lcl(const freesasa_structure *structure, const freesasa_chain_group *chains,
+                                                      const freesasa_classifier *classifier, int options)
+{
+    assert(structure);
+    assert(chains);
+    if (chains->n == 0) return NULL;
+    return get_chains(structure, NULL, chains, classifier, options);
 }
 
 /* ---- accessors (src/structure.c:1083-1424) ------------------------------------------------------------ */
@@ -1320,24 +1367,38 @@ static int chain_index(const freesasa_structure *s, const char *chain)
     return FAIL_MSG("chain '%s' not found", chain);
 }
 /* src/structure.c:1303-1325: a chain's atoms run up to the first atom of the next registered chain */
-int freesasa_structure_chain_atoms(const freesasa_structure *s, char chain, int *first, int *last)
+int freesasa_structure_chain_atoms_lcl(const freesasa_structure *s, const char *chain, int *first, int *last)
 {
-    const char label[2] = {chain, '\0'};
     int c;
     assert(s);
-    if ((c = chain_index(s, label)) < 0) return FAIL_MSG("%s", "");
+    if ((c = chain_index(s, chain)) < 0) return FAIL_MSG("%s", "");
     *first = s->chain_first[c];
     *last = c == s->n_chains - 1 ? s->n - 1 : s->chain_first[c + 1] - 1;
     return FREESASA_SUCCESS;
 }
-int freesasa_structure_chain_residues(const freesasa_structure *s, char chain, int *first, int *last)
+int freesasa_structure_chain_atoms(const freesasa_structure *s, char chain, int *first, int *last)
+{
+    const char label[2] = {chain, '\0'};
+    return freesasa_structure_chain_atoms_lcl(s, label, first, last);
+}
+int freesasa_structure_chain_residues_lcl(const freesasa_structure *s, const char *chain, int *first, int *last)
 {
     int fa, la;
     assert(s);
-    if (freesasa_structure_chain_atoms(s, chain, &fa, &la)) return FAIL_MSG("%s", "");
+    if (freesasa_structure_chain_atoms_lcl(s, chain, &fa, &la)) return FAIL_MSG("%s", "");
     *first = s->res_index[fa];
     *last = s->res_index[la];
     return FREESASA_SUCCESS;
+}
+int freesasa_structure_chain_residues(const freesasa_structure *s, char chain, int *first, int *last)
+{
+    const char label[2] = {chain, '\0'};
+    return freesasa_structure_chain_residues_lcl(s, label, first, last);
+}
+const char *freesasa_structure_residue_chain_lcl(const freesasa_structure *s, int r)
+{
+    RES_OK(s, r);
+    return s->label[s->res_first[r]].chain;
 }
 const char *freesasa_structure_chain_label(const freesasa_structure *s, int index)
 {

@@ -91,6 +91,28 @@ struct freesasa_nodearea {
 };
 #define FREESASA_CONFLICTING_CLASSIFIERS "conflicting-classifiers" /* src/freesasa.h:133 */
 
+/* reference src/freesasa.h:326-376: one _atom_site row of an mmCIF file as the reference's gemmi-based reader hands it over,
+ * and a group of (up to three-character) chain labels */
+struct freesasa_cif_atom {
+    const char *group_PDB;
+    const char auth_asym_id;
+    const char *auth_seq_id, *pdbx_PDB_ins_code, *auth_comp_id, *auth_atom_id, *label_alt_id, *type_symbol;
+    const double Cartn_x, Cartn_y, Cartn_z;
+};
+struct freesasa_cif_atom_lcl {
+    const char *group_PDB, *auth_asym_id, *auth_seq_id, *pdbx_PDB_ins_code, *auth_comp_id, *auth_atom_id, *label_alt_id, *type_symbol;
+    const double Cartn_x, Cartn_y, Cartn_z;
+};
+struct freesasa_chain_group {
+    const char **chains;
+    size_t n;
+};
+#ifndef __cplusplus
+typedef struct freesasa_cif_atom freesasa_cif_atom;
+typedef struct freesasa_cif_atom_lcl freesasa_cif_atom_lcl;
+typedef struct freesasa_chain_group freesasa_chain_group;
+#endif
+
 typedef struct freesasa_classifier freesasa_classifier; /* opaque, src/freesasa.h:345 */
 typedef struct freesasa_structure freesasa_structure;   /* opaque, src/freesasa.h:353 */
 typedef struct freesasa_selection freesasa_selection;   /* opaque, src/freesasa.h:369 */
@@ -130,6 +152,15 @@ int freesasa_structure_add_atom_wopt(freesasa_structure *structure, const char *
                                      const freesasa_classifier *classifier, int options);
 freesasa_structure *freesasa_structure_get_chains(const freesasa_structure *structure, const char *chains,
                                                   const freesasa_classifier *classifier, int options);
+freesasa_structure *freesasa_structure_get_chains_lcl(const freesasa_structure *structure, const freesasa_chain_group *chains,
+                                                      const freesasa_classifier *classifier, int options);
+int freesasa_structure_add_cif_atom(freesasa_structure *structure, freesasa_cif_atom *atom, const freesasa_classifier *classifier,
+                                    int options);
+int freesasa_structure_add_cif_atom_lcl(freesasa_structure *structure, freesasa_cif_atom_lcl *atom,
+                                        const freesasa_classifier *classifier, int options);
+int freesasa_structure_chain_atoms_lcl(const freesasa_structure *structure, const char *chain, int *first, int *last);
+int freesasa_structure_chain_residues_lcl(const freesasa_structure *structure, const char *chain, int *first, int *last);
+const char *freesasa_structure_residue_chain_lcl(const freesasa_structure *structure, int r_i);
 const char *freesasa_structure_chain_labels(const freesasa_structure *structure);
 int freesasa_structure_n(const freesasa_structure *structure);
 int freesasa_structure_n_residues(const freesasa_structure *structure);

@@ -505,3 +505,64 @@ def test_large_file_is_read_in_slices(mine, tmp_path):
         else:
             os.environ["FREESASA_B200_THREADS"] = old
     assert serial["n"] == 60000 and serial["n_chains"] == 5
+
+
+class CifAtomLcl(ctypes.Structure):
+    """struct freesasa_cif_atom_lcl, reference src/freesasa.h:351-363."""
+
+    _fields_ = [(k, ctypes.c_char_p) for k in ("group_PDB", "auth_asym_id", "auth_seq_id", "pdbx_PDB_ins_code", "auth_comp_id",
+                                                 "auth_atom_id", "label_alt_id", "type_symbol")] + \
+               [(k, ctypes.c_double) for k in ("Cartn_x", "Cartn_y", "Cartn_z")]
+
+
+class ChainGroup(ctypes.Structure):
+    _fields_ = [("chains", ctypes.POINTER(ctypes.c_char_p)), ("n", ctypes.c_size_t)]
+
+
+@needs_ref
+def test_long_chain_labels_and_cif_atoms(mine, ref):
+    """The entry points an mmCIF reader uses (src/structure.c:793-829) and the long-chain-label (_lcl) variants
+    (src/structure.c:1012-1081,1303-1378): up to three-character chain labels, insertion codes from a separate column."""
+    rows = []
+    rng = np.random.default_rng(5)
+    for chain, n_res in ((b"AA", 4), (b"B", 3), (b"AB1", 2), (b"AA", 2)):
+        for r in range(n_res):
+            res = [b"ALA", b"GLY", b"HOH", b"UNK"][int(rng.integers(0, 4))]
+            ins = b"?" if r % 3 else b"A"
+            for name, sym in ((b"N", b"N"), (b"CA", b"C"), (b"O", b"O"), (b"XX", b"X")):
+                x, y, z = (float(v) for v in rng.uniform(-20, 20, size=3))
+                rows.append(CifAtomLcl(b"ATOM", chain, b"%d" % (r + 1), ins, res, name, b".", sym, x, y, z))
+    snaps, extra = [], []
+    for api in (mine, ref):
+        L = api.lib
+        L.freesasa_structure_add_cif_atom_lcl.argtypes = [ctypes.c_void_p, ctypes.POINTER(CifAtomLcl), ctypes.c_void_p, ctypes.c_int]
+        L.freesasa_structure_get_chains_lcl.restype = ctypes.c_void_p
+        L.freesasa_structure_get_chains_lcl.argtypes = [ctypes.c_void_p, ctypes.POINTER(ChainGroup), ctypes.c_void_p, ctypes.c_int]
+        for f in ("freesasa_structure_chain_atoms_lcl", "freesasa_structure_chain_residues_lcl"):
+            getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        L.freesasa_structure_residue_chain_lcl.restype = ctypes.c_char_p
+        L.freesasa_structure_residue_chain_lcl.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        s = api.new()
+        rc = [L.freesasa_structure_add_cif_atom_lcl(s.h, ctypes.byref(row), None, st.SKIP_UNKNOWN if k % 5 == 0 else 0) for k, row in enumerate(rows)]
+        a, b = ctypes.c_int(), ctypes.c_int()
+        ranges = []
+        for label in (b"AA", b"B", b"AB1"):
+            ranges.append((L.freesasa_structure_chain_atoms_lcl(s.h, label, ctypes.byref(a), ctypes.byref(b)), a.value, b.value,
+                           L.freesasa_structure_chain_residues_lcl(s.h, label, ctypes.byref(a), ctypes.byref(b)), a.value, b.value))
+        res_chains = [L.freesasa_structure_residue_chain_lcl(s.h, r) for r in range(s.n_residues)]
+        subs = []
+        for group in ([b"AA"], [b"B", b"AB1"], [b"AB1", b"AA", b"B"], [b"ZZ"], [b"AA", b"ZZ"]):
+            arr = (ctypes.c_char_p * len(group))(*group)
+            h = L.freesasa_structure_get_chains_lcl(s.h, ctypes.byref(ChainGroup(arr, len(group))), None, 0)
+            subs.append(snapshot(st.Structure(api, h)) if h else None)
+        labels = [s._call("chain_label", k) for k in range(s.n_chains)]
+        snap = snapshot(s)
+        snap.pop("chains")  # the single-character accessors used by snapshot() cannot address "AA"/"AB1"
+        for sub in subs:
+            if sub:
+                sub.pop("chains")
+        snaps.append(snap)
+        extra.append((rc, ranges, res_chains, subs, labels))
+    assert snaps[0] == snaps[1]
+    assert extra[0] == extra[1]
+    assert extra[0][4] == [b"AA", b"B", b"AB1"] and snaps[0]["n_chains"] == 3
