@@ -8,6 +8,9 @@ Layers (bottom up):
                                     their own names (freesasa_calc_coord, freesasa_calc,
                                     freesasa_lee_richards, freesasa_shrake_rupley, ...), see
                                     include/freesasa_b200_host.h
+* ``structure.py``                  ctypes binding of the structure / classifier / result-tree / selection API of the
+                                    host layer (PDB text -> structure -> SASA -> areas); binds this library or, in
+                                    the tests, the compiled reference through the same code
 * this module                       a thin ctypes mirror of that C interface for Python callers, tests and
                                     bench.py.  ``calc_coord`` goes through the C host layer exactly as a C
                                     program would; ``Engine`` talks to the C ABI directly (explicit
