@@ -567,7 +567,7 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
             if (rel) {
                 const int slot = narc + __popc(b & lt);
                 KeyArc arc;
-                arc.key = (__float_as_int(h[i].st) & ~0xff) | slot;
+                arc.key = (__float_as_int(h[i].st) & ~0x7f) | slot;   // <= 112 arcs here: 7 index bits, ties within 128 ulp
                 arc.en = h[i].en;
                 arcs[slot] = arc;
                 starts[slot] = h[i].st;
@@ -584,7 +584,7 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
                 const int slot = narc + __popc(b & lt);
                 const float st = (float)lane, en = (float)(lane + ones);
                 KeyArc arc;
-                arc.key = (__float_as_int(st) & ~0xff) | slot;
+                arc.key = (__float_as_int(st) & ~0x7f) | slot;
                 arc.en = en;
                 arcs[slot] = arc;
                 starts[slot] = st;

@@ -19,7 +19,7 @@ if "--pdb-rounded" in sys.argv:  # what a PDB file holds: 3 decimals (exact tang
     r = np.round(r, 2)
 eng = fs.Engine(0)
 out = {"atoms": n, "pdb_rounded": "--pdb-rounded" in sys.argv, "cases": {}}
-for slices in (5, 10, 20, 50, 100):
+for slices in ((5, 20) if "--quick" in sys.argv else (5, 10, 20, 50, 100)):
     got = eng.calc(fs.LEE_RICHARDS, x, r, 1.4, slices)
     want = ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, slices)
     err = np.abs(got - want)
