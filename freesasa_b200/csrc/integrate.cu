@@ -281,9 +281,10 @@ __device__ __forceinline__ double lr_atom(const Rec4<T> *recs, Arc<T> *arcs, int
 // replaced:
 //   * alpha = 2 atan(sqrt(q)) with q = min(N,D)/max(N,D) in [0,1], N = f1 f2, D = f3 (a+b+d), via
 //     MUFU rcp/sqrt and a degree-7 minimax polynomial in q (|err| < 1.5e-7 rad), reflected for N > D;
-//   * every arc gets a UNIQUE integer sort key = (bits(start) & ~0xff) | arc index, so "arc m comes
-//     before arc k" is one integer compare; two starts within 256 ulp (6e-5 rad) may swap order,
-//     which changes the union only by that sliver and only in the ~1e-3 of slices where it happens.
+//   * every arc gets a UNIQUE integer sort key = (bits(start) & ~0xff) | arc index (7 index bits in the
+//     <= 96-neighbour path, which never holds more than 112 arcs), so "arc m comes before arc k" is one integer
+//     compare; two starts within 256 (128) ulp may swap order, which changes the union only by that sliver
+//     (<= 1e-4 rad) and only in the ~1e-3 of slices where it happens.
 //     The exact start (kept in a side array) is still what the exposed gap is measured from.
 __device__ __forceinline__ float fast_rcp(float x)
 {
