@@ -92,8 +92,7 @@ static inline void atom_area(freesasa_nodearea *area, double a, int is_bb, int c
 int freesasa_atom_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
                            int atom_index)
 {
-    atom_area(area, result->sasa[atom_index], freesasa_atom_is_backbone(structure->label[atom_index].name),
-              structure->cls[atom_index]);
+    atom_area(area, result->sasa[atom_index], FSB_CLS_BACKBONE(structure->cls[atom_index]), FSB_CLS_CLASS(structure->cls[atom_index]));
     return FREESASA_SUCCESS;
 }
 
@@ -194,11 +193,11 @@ static void build_part(int part, int n_parts, void *arg)
         a->parent = &q->res_nodes[s->res_index[i]];
         a->children = NULL;
         a->next = a + 1; /* the last atom of each residue is cut below */
-        a->p.atom.is_polar = s->cls[i] == FREESASA_ATOM_POLAR;
-        a->p.atom.is_bb = freesasa_atom_is_backbone(l->name);
+        a->p.atom.is_polar = FSB_CLS_CLASS(s->cls[i]) == FREESASA_ATOM_POLAR;
+        a->p.atom.is_bb = FSB_CLS_BACKBONE(s->cls[i]); /* decided once per distinct name while reading */
         a->p.atom.index = i;
         a->p.atom.radius = s->radius[i];
-        atom_area(a->area, q->result->sasa[i], a->p.atom.is_bb, s->cls[i]); /* name stays NULL, as in src/node.c:269-270 */
+        atom_area(a->area, q->result->sasa[i], a->p.atom.is_bb, FSB_CLS_CLASS(s->cls[i])); /* name stays NULL, as in src/node.c:269-270 */
     }
     for (r = r0; r < r1; ++r) {
         freesasa_node *res = &q->res_nodes[r];

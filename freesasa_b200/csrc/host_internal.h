@@ -66,7 +66,7 @@ struct freesasa_structure {
     double *radius;
     struct atom_label *label;
     int *res_index;
-    unsigned char *cls;
+    unsigned char *cls; /* bits 0-1: freesasa_atom_class, bit 2: backbone atom (freesasa_atom_is_backbone of the name) */
     /* PDB lines are not copied while reading: the structure keeps a reference to the text it was read from and a
      * slice per atom; NUL-terminated copies are made only if somebody asks for them (atom_pdb_line) */
     struct shared_text *text;
@@ -85,8 +85,14 @@ struct freesasa_structure {
     int *chain_first;
     char *classifier_name;
     const freesasa_classifier *last_classifier; /* classifier of the previous add: skips re-registering its name */
+    /* direct-mapped memo of freesasa_atom_is_backbone() by the four name bytes (a structure has a few dozen names) */
+    unsigned int bb_key[64];
+    unsigned char bb_val[64];
     int model;
 };
 
+
+#define FSB_CLS_CLASS(c) ((c)&3)
+#define FSB_CLS_BACKBONE(c) (((c) >> 2) & 1)
 
 #endif

@@ -234,7 +234,21 @@ static int add_atom(freesasa_structure *s, const struct atom_label *a, const dou
         ++s->n_res;
     }
     s->label[i] = *a;
-    s->cls[i] = (unsigned char)(row >= 0 ? fsb_classifier_row_class(classifier, row) : FREESASA_ATOM_UNKNOWN);
+    {
+        unsigned int key;
+        unsigned slot;
+        int bb;
+        memcpy(&key, a->name, 4);
+        slot = (key * 2654435761u) >> 26;
+        if (s->bb_key[slot] == key && key != 0) {
+            bb = s->bb_val[slot];
+        } else {
+            bb = freesasa_atom_is_backbone(a->name);
+            s->bb_key[slot] = key;
+            s->bb_val[slot] = (unsigned char)bb;
+        }
+        s->cls[i] = (unsigned char)((row >= 0 ? fsb_classifier_row_class(classifier, row) : FREESASA_ATOM_UNKNOWN) | (bb << 2));
+    }
     s->res_index[i] = s->n_res - 1;
     s->radius[i] = r;
     s->line_at[i] = line ? line - s->text->data : -1;
@@ -1311,7 +1325,7 @@ const char *freesasa_structure_atom_chain_lcl(const freesasa_structure *s, int i
 const char *freesasa_structure_atom_symbol(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->label[i].symbol; }
 double freesasa_structure_atom_radius(const freesasa_structure *s, int i) { ATOM_OK(s, i); return s->radius[i]; }
 void freesasa_structure_atom_set_radius(freesasa_structure *s, int i, double radius) { ATOM_OK(s, i); s->radius[i] = radius; }
-freesasa_atom_class freesasa_structure_atom_class(const freesasa_structure *s, int i) { ATOM_OK(s, i); return (freesasa_atom_class)s->cls[i]; }
+freesasa_atom_class freesasa_structure_atom_class(const freesasa_structure *s, int i) { ATOM_OK(s, i); return (freesasa_atom_class)FSB_CLS_CLASS(s->cls[i]); }
 /* src/structure.c:1199-1206: the line as fgets() delivered it (with its newline), NULL for atoms added by hand.
  * The NUL-terminated copies are built for the whole structure on the first call. */
 const char *freesasa_structure_atom_pdb_line(const freesasa_structure *s, int i)
