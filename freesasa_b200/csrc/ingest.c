@@ -898,19 +898,17 @@ static int from_range_parallel(const struct shared_text *t, long begin, long end
             s->n_res = n_res;
             s->n = s->coord.n = total;
             /* phase 2: every fragment is copied into place by its own thread (first touch of the final arrays in parallel) */
-            started = 0;
-            for (k = 1; k < used; ++k) {
-                if (job[k].dst == NULL) continue;
-                if (pthread_create(&thread[k], NULL, chunk_copy, &job[k]) != 0) {
-                    chunk_copy(&job[k]);
-                    thread[k] = 0;
-                } else {
-                    ++started;
+            {
+                int spawned[PARALLEL_MAX_THREADS] = {0};
+                for (k = 1; k < used; ++k) {
+                    if (job[k].dst == NULL) continue;
+                    spawned[k] = pthread_create(&thread[k], NULL, chunk_copy, &job[k]) == 0;
+                    if (!spawned[k]) chunk_copy(&job[k]);
                 }
+                if (job[0].dst) chunk_copy(&job[0]);
+                for (k = 1; k < used; ++k)
+                    if (spawned[k]) pthread_join(thread[k], NULL);
             }
-            if (job[0].dst) chunk_copy(&job[0]);
-            for (k = 1; k < used; ++k)
-                if (job[k].dst && thread[k]) pthread_join(thread[k], NULL);
         }
     }
     if (failed >= 0) {

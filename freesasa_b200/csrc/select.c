@@ -142,6 +142,7 @@ struct parse {
     const freesasa_structure *s;
     int n;
     int dry; /* syntax check only: the reference parses the whole command before it evaluates (and warns about) anything */
+    int depth; /* nesting of parentheses and "not": bounded, so that a hostile command cannot exhaust the stack */
     int warn, err;
 };
 
@@ -309,19 +310,26 @@ static int parse_items(struct parse *ps, enum selector sel, unsigned char *mask)
 static int parse_or(struct parse *ps, unsigned char *mask);
 
 /* not-level and primaries */
+#define MAX_NESTING 200
 static int parse_unary(struct parse *ps, unsigned char *mask)
 {
-    int i;
+    int i, ok;
     enum selector sel;
     switch (ps->sc.tok) {
     case T_NOT:
+        if (++ps->depth > MAX_NESTING) return 0;
         next_token(&ps->sc);
-        if (!parse_unary(ps, mask)) return 0;
+        ok = parse_unary(ps, mask);
+        --ps->depth;
+        if (!ok) return 0;
         for (i = 0; i < ps->n; ++i) mask[i] = !mask[i];
         return 1;
     case T_LPAR:
+        if (++ps->depth > MAX_NESTING) return 0;
         next_token(&ps->sc);
-        if (!parse_or(ps, mask)) return 0;
+        ok = parse_or(ps, mask);
+        --ps->depth;
+        if (!ok) return 0;
         if (ps->sc.tok != T_RPAR) return 0;
         next_token(&ps->sc);
         return 1;

@@ -178,3 +178,13 @@ def test_selections_on_structure_nodes(world):
         seen.append(got)
         assert tree.free(root) == 0
     assert seen[0] == seen[1] and len(seen[0]) == 2 and seen[0][0][2] > 0
+
+
+def test_hostile_nesting_is_rejected_not_crashed(world):
+    (sm, s, r, _), _ = world
+    deep = ("s, " + "(" * 5000 + "resn ALA" + ")" * 5000).encode()
+    assert sm.run(deep, s, r)[0] is None
+    nots = ("s, " + "not " * 5000 + "resn ALA").encode()
+    assert sm.run(nots, s, r)[0] is None
+    ok = ("s, " + "(" * 150 + "resn ALA" + ")" * 150).encode()
+    assert sm.run(ok, s, r)[0] is not None
