@@ -65,14 +65,15 @@ def digest(snap) -> str:
     return hashlib.sha256(repr(snap).encode()).hexdigest()
 
 
-def same_structure(mine, ref, text, classifier=None, options=0):
+def same_structure(mine, ref, text, classifier=None, options=0, ignore=()):
     a = mine.from_pdb(text, mine.classifier(classifier) if classifier else None, options)
     b = ref.from_pdb(text, ref.classifier(classifier) if classifier else None, options)
     sa, sb = snapshot(a), snapshot(b)
     assert (sa is None) == (sb is None)
     if sa is not None:
         for key in sb:
-            assert sa[key] == sb[key], key
+            if key not in ignore:
+                assert sa[key] == sb[key], key
     return sa
 
 
@@ -210,7 +211,9 @@ def test_edge_cases(mine, ref, tag):
     for options in OPTION_SETS:
         if tag in NO_OCCUPANCY and options & st.RADIUS_FROM_OCCUPANCY:
             continue
-        same_structure(mine, ref, text, None, options)
+        # a MODEL record shorter than 11 characters makes the reference sscanf() past the end of the line into whatever
+        # its fgets() buffer held before (src/structure.c:710): its model number is then arbitrary; here it stays 1
+        same_structure(mine, ref, text, None, options, ignore=("model",) if tag == "model_short" else ())
 
 
 def test_missing_occupancy_fails_cleanly(mine):
