@@ -569,3 +569,38 @@ def test_long_chain_labels_and_cif_atoms(mine, ref):
     assert snaps[0] == snaps[1]
     assert extra[0] == extra[1]
     assert extra[0][4] == [b"AA", b"B", b"AB1"] and snaps[0]["n_chains"] == 3
+
+
+def test_decimal_fast_paths_equal_strtod(mine):
+    """The coordinate parser's claim (ingest.c: strict_coords / fast_coords): integer mantissa / power of ten, ONE IEEE
+    division, is the correctly rounded value — i.e. what strtod (and Python's float()) return.  80 000 records in the
+    %8.3f layout over its whole range (240 000 numbers) and 13 000 records of free-format tokens with 1..15 digits."""
+    rng = np.random.default_rng(2024)
+    template = w.pdb_atom_line(1, "CA", "ALA", "A", 1, 0.0, 0.0, 0.0, "C")
+    lines, want = [], []
+    specials = [0.0, -0.0, 0.001, -0.001, 999.999, -999.999, 0.1, 0.7, 123.5, -0.0004, 0.0005]
+    for k in range(80000):
+        first = rng.uniform(-999.999, 9999.999) if k % 4 else float(rng.integers(-999, 9999))
+        rest = rng.uniform(-999.999, 999.999, size=2) if k % 7 else rng.choice(specials, size=2)
+        trio = ["%8.3f" % v for v in (first, *rest)]
+        lines.append(template[:30] + "".join(trio) + template[54:])       # the fixed-column layout, fields may touch
+        want.append([float(t) for t in trio])
+    for k in range(13000):
+        trio = []
+        for _ in range(3):
+            digits = int(rng.integers(1, 8 if k % 3 else 16))
+            frac = int(rng.integers(0, digits + 1))
+            m = "".join(str(d) for d in rng.integers(0, 10, size=digits))
+            tok = (m[: digits - frac].lstrip("0") or "0") + ("." + m[digits - frac:] if frac else "")
+            if k % 11 == 0 and frac:
+                tok = tok[1:] if tok.startswith("0.") else tok                  # ".5" style
+            trio.append(("-" if rng.random() < 0.4 else "+" if rng.random() < 0.05 else "") + tok)
+        section = " ".join(trio)
+        if len(section) > 24:
+            continue
+        lines.append(template[:30] + section.ljust(24) + template[54:])    # what sscanf("%lf%lf%lf") reads
+        want.append([float(t) for t in trio])
+    text = ("\n".join(lines) + "\n").encode()
+    s = mine.from_pdb(text)
+    assert s.n == len(lines) > 85000
+    np.testing.assert_array_equal(s.xyz().view(np.uint64), np.array(want).view(np.uint64))   # bit for bit, signed zeros included
