@@ -16,6 +16,10 @@
  *                                                        one correctly rounded division == strtod), sscanf only for
  *                                                        exotic tokens (exponents, hex, inf/nan, > 15 digits)
  *   linear scan over all chains per atom                 previous atom's chain first
+ *   one thread                                           files >= 4 MB fetched with pread slices, ranges >= 1 MB parsed as
+ *                                                        one chunk per core and stitched; the models / chains of
+ *                                                        freesasa_structure_array() parsed concurrently (messages replayed
+ *                                                        in file order: the output is the serial one)
  *
  * Everything observable is kept, including the quirks: which lines count as atoms (src/structure.c:662-666), the
  * hydrogen test that only fires on lines long enough to carry an element symbol (src/pdb.c:260-283), "first
