@@ -125,3 +125,21 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".inc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU", ""), os.path.join(dirpath, f)
+
+
+def test_public_headers_compile_as_c99_and_cxx14(tmp_path):
+    """include/freesasa.h (the forwarding header), freesasa_b200_host.h and fsb200.h are valid strict C99 and C++14."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    c = os.path.join(tmp_path, "t.c")
+    cxx = os.path.join(tmp_path, "t.cpp")
+    body = ('#include "freesasa.h"\n#include "fsb200.h"\n'
+            "int main(void) { freesasa_parameters p = freesasa_default_parameters; freesasa_nodearea a = freesasa_nodearea_null;\n"
+            "  freesasa_chain_group g = {0, 0}; (void)p; (void)a; (void)g; return FREESASA_ATOM_POLAR == 1 ? 0 : 1; }\n")
+    open(c, "w").write(body)
+    open(cxx, "w").write(body)
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror",
+                    "-I", inc, "-fsyntax-only", c], check=True)
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", inc,
+                    "-fsyntax-only", cxx], check=True)
