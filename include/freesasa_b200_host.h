@@ -15,7 +15,12 @@
  * these calls can link this library instead of libfreesasa; a full FreeSASA build swaps its
  * src/sasa_lr.c + src/sasa_sr.c + src/nb.c for the shim in INTEGRATION.md and keeps everything else.
  *
- * Additive (not in the reference): freesasa_calc_coord_batch().
+ * Around that path, the same library provides the host rows of SURVEY.md §8(f) under the reference's names, each
+ * declaration below citing the lines it mirrors: classifiers (csrc/radii.c), structures and PDB reading (csrc/ingest.c),
+ * the result tree, class sums and the PDB writer (csrc/areas.c), selections (csrc/select.c).  Results are bit-identical to
+ * the reference's.
+ *
+ * Additive (not in the reference): freesasa_calc_coord_batch(), freesasa_calc_structure_batch(), freesasa_calc_tree_batch().
  */
 #ifndef FREESASA_B200_HOST_H
 #define FREESASA_B200_HOST_H
