@@ -46,6 +46,13 @@ def test_structure_example_compiles_and_links():
     assert os.path.exists(EXE_S)
 
 
+def test_models_example_compiles_and_links(tmp_path):
+    """examples/example_models.c: freesasa_structure_array() + the additive freesasa_calc_tree_batch()."""
+    exe = os.path.join(tmp_path, "example_models")
+    _compile(os.path.join(ROOT, "examples", "example_models.c"), exe)
+    assert os.path.exists(exe)
+
+
 @pytest.mark.skipif(not os.path.exists(REF_EXAMPLE), reason="reference tree not present")
 def test_reference_example_program_compiles_unmodified(tmp_path):
     """The reference's own src/example.c (freesasa_structure_from_pdb -> freesasa_calc_structure ->
