@@ -1040,7 +1040,8 @@ static int find_models(const struct shared_text *t, struct range **out)
                 m = p;
             }
             m[n].begin = pos;
-            m[n].end = 0;
+            m[n].end = t->len; /* a MODEL without its ENDMDL (truncated file) runs to the end of the text; the reference
+                                * leaves this field uninitialised (src/pdb.c:63-73) and does whatever the heap held */
             ++n;
         }
         if (len >= 6 && memcmp(l, "ENDMDL", 6) == 0) {

@@ -269,7 +269,8 @@ def test_structure_array(mine, ref, options):
     texts = [w.pdb_text(150, seed=31, chains=3, models=4, hydrogens=0.1, hetatm=2).encode(),
              w.pdb_text(150, seed=32, chains=2, models=1, hetatm=1).encode(),
              EDGE_TEXTS["endmdl_first"].encode(), EDGE_TEXTS["model_short"].encode(), EDGE_TEXTS["no_atoms"].encode(),
-             EDGE_TEXTS["chain_returns"].encode(), b"MODEL        1\n" + atom().encode() + b"\n"]
+             EDGE_TEXTS["chain_returns"].encode()]  # (a MODEL without ENDMDL is undefined in the reference: see
+    #                                          test_truncated_ensemble_keeps_its_last_model)
     for text in texts:
         a, b = mine.array(text, None, options), ref.array(text, None, options)
         assert (a is None) == (b is None)
@@ -604,3 +605,14 @@ def test_decimal_fast_paths_equal_strtod(mine):
     s = mine.from_pdb(text)
     assert s.n == len(lines) > 85000
     np.testing.assert_array_equal(s.xyz().view(np.uint64), np.array(want).view(np.uint64))   # bit for bit, signed zeros included
+
+
+def test_truncated_ensemble_keeps_its_last_model(mine):
+    """A file that ends inside a MODEL (no ENDMDL): the last model runs to the end of the text.  (The reference leaves
+    that model's end uninitialised, src/pdb.c:63-73, so there is nothing to compare with.)"""
+    text = w.pdb_text(60, seed=3, chains=2, models=3).encode()
+    cut = text[: text.rindex(b"ENDMDL")]
+    models = mine.array(cut, None, st.SEPARATE_MODELS)
+    assert [m.n for m in models] == [60, 60, 60] and [m.model for m in models] == [1, 2, 3]
+    full = mine.array(text, None, st.SEPARATE_MODELS)
+    assert snapshot(models[2]) == snapshot(full[2])
