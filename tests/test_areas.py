@@ -242,3 +242,39 @@ def test_trees_of_a_batch_built_concurrently(both):
         p = fs.default_parameters()
         assert H.freesasa_calc_tree_batch(n, handles, ctypes.byref(p), names, trees) == -1
         assert not any(trees[k] for k in range(n))
+
+
+@needs_ref
+def test_write_pdb_without_pdb_lines_fails_in_both(both, tmp_path):
+    """Atoms added by hand carry no PDB record: freesasa_write_pdb() reports failure (src/pdb.c:318-320); trees with several
+    results (freesasa_tree_add_result twice) are written result by result."""
+    import os
+
+    outputs = []
+    for api, tree in both:
+        L = api.lib
+        L.freesasa_write_pdb.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        s = api.new()
+        for k, name in enumerate((b" N  ", b" CA ", b" C  ")):
+            s.add_atom(name, b"ALA", b"   1 ", b"A", 1.5 * k, 0.0, 0.0)
+        result, keep = tree.make_result(np.array([1.0, 2.0, 3.0]))
+        root = tree.init(result, s, b"hand")
+        fp = st._libc.fopen(os.path.join(tmp_path, "x.pdb").encode(), b"w")
+        rc_fail = L.freesasa_write_pdb(fp, root)
+        st._libc.fclose(fp)
+        tree.free(root)
+        text = w.pdb_text(60, seed=2, chains=2).encode()
+        s1, s2 = api.from_pdb(text), api.from_pdb(w.pdb_text(40, seed=3).encode())
+        r1, k1 = tree.make_result(np.linspace(0, 9, s1.n))
+        r2, k2 = tree.make_result(np.linspace(3, 5, s2.n))
+        root = tree.init(r1, s1, b"one")
+        assert L.freesasa_tree_add_result(root, ctypes.byref(r2), s2.h, b"two") == 0
+        path = os.path.join(tmp_path, "y.pdb")
+        fp = st._libc.fopen(path.encode(), b"w")
+        rc_ok = L.freesasa_write_pdb(fp, root)
+        st._libc.fclose(fp)
+        tree.free(root)
+        outputs.append((rc_fail, rc_ok, open(path, "rb").read().split(b"\n")[1:]))
+    assert outputs[0] == outputs[1]
+    assert outputs[0][0] == -1 and outputs[0][1] == 0
+    assert sum(ln.startswith(b"MODEL") for ln in outputs[0][2]) == 2
