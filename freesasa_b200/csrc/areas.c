@@ -755,3 +755,50 @@ int freesasa_write_pdb(FILE *output, freesasa_node *root)
             if (write_structure_pdb(output, structure) == FREESASA_FAIL) return FAIL_MSG("%s", "");
     return FREESASA_SUCCESS;
 }
+
+/* ---- per-residue-type and per-residue listings (src/log.c:150-246; the CLI's --format=res / --format=seq) ------------- */
+int freesasa_write_res(FILE *log, freesasa_node *root)
+{
+    const int n_types = freesasa_classify_n_residue_types() + 1;
+    double *area = malloc(sizeof(double) * (size_t)n_types);
+    freesasa_node *result, *structure, *chain, *residue;
+    int i;
+    assert(log);
+    assert(root);
+    assert(root->type == FREESASA_NODE_ROOT);
+    if (area == NULL) return MEM_FAIL();
+    for (result = root->children; result; result = result->next) {
+        for (i = 0; i < n_types; ++i) area[i] = 0;
+        for (structure = result->children; structure; structure = structure->next)
+            for (chain = structure->children; chain; chain = chain->next)
+                for (residue = chain->children; residue; residue = residue->next)
+                    area[freesasa_classify_residue(residue->name)] += residue->area->total; /* in tree order, as the reference */
+        fprintf(log, "# Residue types in %s\n", result->name);
+        for (i = 0; i < n_types - 1; ++i)
+            if (i < 20 || area[i] > 0) fprintf(log, "RES %s : %10.2f\n", freesasa_classify_residue_name(i), area[i]);
+        fprintf(log, "\n");
+    }
+    free(area);
+    fflush(log);
+    if (ferror(log)) return FAIL_MSG("write error");
+    return FREESASA_SUCCESS;
+}
+
+int freesasa_write_seq(FILE *log, freesasa_node *root)
+{
+    freesasa_node *result, *structure, *chain, *residue;
+    assert(log);
+    assert(root);
+    assert(root->type == FREESASA_NODE_ROOT);
+    for (result = root->children; result; result = result->next) {
+        fprintf(log, "# Residues in %s\n", result->name);
+        for (structure = result->children; structure; structure = structure->next)
+            for (chain = structure->children; chain; chain = chain->next)
+                for (residue = chain->children; residue; residue = residue->next)
+                    fprintf(log, "SEQ %s %s %s : %7.2f\n", chain->name, residue->p.residue.number, residue->name, residue->area->total);
+        fprintf(log, "\n");
+    }
+    fflush(log);
+    if (ferror(log)) return FAIL_MSG("write error");
+    return FREESASA_SUCCESS;
+}

@@ -239,6 +239,28 @@ int freesasa_atom_is_backbone(const char *atom_name)
     return 0;
 }
 
+/* Residue types for the per-type sums of freesasa_write_res() (src/classifier.c:1020-1088): the twenty amino acids first
+ * (always listed), then non-standard ones, "UNK" (everything not recognised), capping groups and nucleotides. */
+static const char *const residue_type_name[] = {
+    "ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL",
+    "CSE", "SEC", "PYL", "PYH", "ASX", "GLX", "UNK", "ACE", "NH2", "DA", "DC", "DG", "DT", "DU", "DI", "A", "C", "G", "U", "I", "T", "N"};
+#define RESIDUE_TYPE_UNKNOWN 26
+int freesasa_classify_n_residue_types(void) { return COUNT(residue_type_name); }
+const char *freesasa_classify_residue_name(int residue_type)
+{
+    assert(residue_type >= 0 && residue_type < COUNT(residue_type_name));
+    return residue_type_name[residue_type];
+}
+int freesasa_classify_residue(const char *res_name)
+{
+    const char *r;
+    const int len = fsb_token(res_name, &r);
+    int i;
+    for (i = 0; i < COUNT(residue_type_name); ++i)
+        if (len > 0 && same(residue_type_name[i], r, len)) return i;
+    return RESIDUE_TYPE_UNKNOWN;
+}
+
 /* ---- user configuration files (src/classifier.c:164-735; format: doc/doxy-main.md "Classifier configuration") -- */
 #define CFG_LINE 256 /* MAX_LINE_LEN, src/classifier.c:18 */
 

@@ -273,6 +273,13 @@ int freesasa_select_area(const char *command, char *name, double *area, const fr
 /* row f-4, per-atom writer: reference src/freesasa_internal.h:200, src/pdb.c:347-375 (what the CLI's --format=pdb and
  * freesasa_tree_export(..., FREESASA_PDB) emit) */
 int freesasa_write_pdb(FILE *output, freesasa_node *root);
+/* per-residue-type and per-residue listings, reference src/freesasa_internal.h:176-190, src/log.c:150-246 (the CLI's
+ * --format=res / --format=seq, pinned by the reference's tests/data/restype.reference and seq.reference) */
+int freesasa_write_res(FILE *log, freesasa_node *root);
+int freesasa_write_seq(FILE *log, freesasa_node *root);
+int freesasa_classify_n_residue_types(void);
+int freesasa_classify_residue(const char *res_name);
+const char *freesasa_classify_residue_name(int residue_type);
 extern const char *freesasa_string;
 /* reference src/freesasa_internal.h (used by the tree and the writers) */
 int freesasa_atom_nodearea(freesasa_nodearea *area, const freesasa_structure *structure, const freesasa_result *result,
