@@ -355,3 +355,35 @@ def test_published_class_sums(both, pdb_fixtures, name, key, total, polar, apola
     assert got[0] == b"whole-structure"
     assert abs(f(got[1]) - total) < 1e-5 and abs(f(got[4]) - polar) < 1e-5 and abs(f(got[5]) - apolar) < 1e-5
     assert f(got[6]) == 0.0  # nothing unknown
+
+
+@pytest.mark.parametrize("classifier", ["protor", "naccess"])
+def test_published_relative_areas_of_tripeptides(both, classifier):
+    """SURVEY.md §8(c) pin (tests/test-cli.in:309-322): for each GLY-X-GLY tripeptide of tests/data/rsa/, Lee-Richards with
+    1000 slices and the ProtOr or NACCESS radii gives residue X exactly 100.0 % of the classifier's reference areas (all
+    atoms, side chain, main chain, apolar, polar — printed with one decimal).  Checks the residue reference tables, the
+    classes and the tree's residue sums of this repo; the per-atom areas come from the CPU restatement."""
+    import glob
+    import os
+
+    files = sorted(glob.glob("/root/reference/tests/data/rsa/*.pdb"))
+    if not files:
+        pytest.skip("reference test data not present")
+    (mine, tm), _ = both
+    L = mine.lib
+    for path in files:
+        s = mine.from_pdb_path(path, mine.classifier(classifier))
+        sasa = ob.oracle_calc(s.xyz(), s.radii(), ob.LEE_RICHARDS, 1.4, 1000)
+        result, keep = tm.make_result(sasa)
+        root = tm.init(result, s, b"rsa")
+        chain = L.freesasa_node_children(L.freesasa_node_children(L.freesasa_node_children(root)))
+        residue = L.freesasa_node_next(L.freesasa_node_children(chain))           # residue 2 of the tripeptide
+        assert L.freesasa_node_name(residue).decode() == os.path.basename(path)[:3]
+        area, ref = L.freesasa_node_area(residue).contents, L.freesasa_node_residue_reference(residue).contents
+        for field in ("total", "side_chain", "main_chain", "apolar", "polar"):
+            absolute, reference = getattr(area, field), getattr(ref, field)
+            if reference == 0.0:                                                    # GLY has no side chain: "N/A"
+                assert field == "side_chain" and "GLY" in path
+                continue
+            assert "%.1f" % (100.0 * absolute / reference) == "100.0", (path, field, absolute, reference)
+        tm.free(root)
