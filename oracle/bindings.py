@@ -31,7 +31,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 
 def build(ref: bool = True) -> None:
     """(Re)build liboracle.so and, when the reference tree is present, _ref/."""
-    targets = ["oracle"] + (["ref"] if ref else [])
+    targets = ["oracle"] + (["ref", "patched"] if ref else [])
     subprocess.run(["make", "-C", HERE, "-s"] + targets, check=True)
 
 
