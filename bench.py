@@ -4,23 +4,31 @@ n_slices=100, 100k-atom synthetic globule; max |dSASA| vs the reference).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA engine
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+    python bench.py --alg sr                                 # config C3 (Shrake-Rupley, 1000 points) instead of C2
 
-A "step" is one pass of the hot path (cell list build + Lee-Richards integration of every atom) over
-one structure per GPU.  N=1: config C2.  N>1 (launched by torch.distributed.run, one rank per GPU):
-every rank integrates its own 100k-atom structure (weak scaling: work per GPU fixed) and the step ends
-with ONE NCCL all-gather of the per-atom SASA of all ranks; value = atoms of all ranks / max-over-ranks time.
+A "step" is one pass of the hot path (cell list build + integration of every atom) over one structure per GPU.
+N=1: config C2.  N>1 (launched by torch.distributed.run, one rank per GPU): every rank integrates its own 100k-atom
+structure (weak scaling: work per GPU fixed) and the step ends with the all-gather of the per-atom SASA of all ranks;
+value = atoms of all ranks / max-over-ranks time.  The all-gather is FUSED into the integration kernel: every rank's
+kernel stores each area into the symmetric result buffer of every rank (peer memory over NVLink, CUDA IPC), framed by two
+one-warp flag barriers in peer memory — no NCCL call and no host synchronisation between the kernel and the exchange
+(`--collective nccl` runs the plain variant: kernels enqueued, one ncclAllGather queued behind them, one synchronisation).
 
 Reported numbers
   value    atoms/s with the inputs already resident in HBM; device time from CUDA events on the stream
            the kernels are launched on; L2 flushed (256 MiB write) between timed steps.
   e2e      atoms/s through the reference-facing call freesasa_calc_coord() of the C host layer with
            HOST buffers (N=1), i.e. H2D of xyz+radii and D2H of the areas inside the timed region
-           (N>1: pinned host -> device -> compute -> all-gather -> host on every rank).
+           (N>1: pinned host -> device -> compute + fused all-gather -> host).
   roofline algorithmic bytes (40 B/atom: 24 B xyz + 8 B radius in, 8 B area out) / integrate-kernel
            time vs the measured HBM copy bandwidth.  The integration kernel is FP32-issue bound, not
            HBM bound (~5.5e3 circle-circle evaluations per atom), so this fraction is tiny by
-           construction; `compute` adds pair-slice evaluations/s.
+           construction; `issue` carries the figure that measures the kernel: warp instructions (committed ncu
+           capture) / kernel time / issue slots; `compute` the executed and the effective pair-slice rates.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref) on this box's host cores, same arrays.
+  ablation, surface_workload, c3, configs   (N=1 run, rank 0): the same engine without the buried-atom certificate, on a
+           protein-like surface fraction (1M-atom shell), on config C3, and configs C4 / C5 of BASELINE.json through the
+           multi-GPU C entry point fsb200_calc_multi() on 1 and on all visible GPUs, each with parity against the oracle.
 """
 import argparse
 import json
@@ -35,17 +43,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ATOMS = 100_000
-N_SLICES = 100
 PROBE = 1.4
 ALG_BYTES_PER_ATOM = 40.0
-# DRAM traffic of the dominant kernel, from the committed ncu --set full capture of this same command
-# (bench.py --steps 2 --warmup 3): 6.00 MB read + 0.0 KB written per launch for 100k atoms = 60 B/atom,
-# i.e. the 32 B/atom sorted double4 records are fetched about once (plus the item queue, the permutation and the L2-flushed
-# output lines) and everything else stays in L2/shared memory.
-NCU_DRAM_BYTES_PER_LAUNCH = 6001920
-NCU_SOURCE = "profiles/r1_15_lr_cert_antipodal_hybrid.txt"
-METRIC = "atoms/sec (LR n_slices=100)"
-WORKLOAD = "C2: 100k-atom synthetic globular coord array, Lee-Richards n_slices=100, probe 1.4 A"
+# From the committed ncu --set full capture of this same command (profiles/, see NCU_SOURCE): DRAM traffic and warp
+# instructions of ONE launch of the dominant kernel on the C2 workload.  Re-derived whenever the kernel changes.
+NCU = {
+    "lr": {"dram_bytes_per_launch": 6001920, "warp_instructions_per_launch": 365953831,
+           "source": "profiles/r1_15_lr_cert_antipodal_hybrid.txt"},
+    "sr": {"dram_bytes_per_launch": None, "warp_instructions_per_launch": None, "source": None},
+}
+try:  # the current round's capture, written by profiles/summarize.py --json
+    with open(os.path.join(ROOT, "profiles", "ncu_current.json")) as _f:
+        for _k, _v in json.load(_f).items():
+            NCU[_k].update(_v)
+except Exception:
+    pass
+
+ALGS = {
+    "lr": {"alg": 0, "resolution": 100, "metric": "atoms/sec (LR n_slices=100)", "kernel": "k_integrate<LR,float>",
+           "workload": "C2: 100k-atom synthetic globular coord array, Lee-Richards n_slices=100, probe 1.4 A"},
+    "sr": {"alg": 1, "resolution": 1000, "metric": "atoms/sec (SR n_points=1000)", "kernel": "k_integrate<SR,float>",
+           "workload": "C3: 100k-atom synthetic globular coord array, Shrake-Rupley n_points=1000, probe 1.4 A"},
+}
 
 
 def host_threads():
@@ -60,6 +79,11 @@ def measured_peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def shared_config(spec):
+    """The `config` object: identical in both arms so that the driver can compare them key by key."""
+    return {"workload": spec["workload"], "atoms_per_gpu": N_ATOMS, "resolution": spec["resolution"], "probe_radius": PROBE}
 
 
 class ClockSampler:
@@ -115,21 +139,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_run(xyz, radii, threads):
+def cpu_reference_run(xyz, radii, threads, spec):
     """One pass of the reference's own CPU implementation (oracle/_ref when built, else our C port)."""
     from oracle import bindings as ob
 
     if ob.ref_available():
         ob.ref_lib().freesasa_set_verbosity(1)
         t = time.perf_counter()
-        sasa = ob.ref_calc(xyz, radii, ob.LEE_RICHARDS, PROBE, N_SLICES, threads)
+        sasa = ob.ref_calc(xyz, radii, spec["alg"], PROBE, spec["resolution"], threads)
         return time.perf_counter() - t, sasa, "reference"
     t = time.perf_counter()
-    sasa = ob.oracle_calc(xyz, radii, ob.LEE_RICHARDS, PROBE, N_SLICES, threads)
+    sasa = ob.oracle_calc(xyz, radii, spec["alg"], PROBE, spec["resolution"], threads)
     return time.perf_counter() - t, sasa, "port"
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, spec):
     if rank != 0:
         return
     from freesasa_b200 import workloads
@@ -137,18 +161,20 @@ def run_reference_arm(args, rank):
     xyz, radii = workloads.globule(N_ATOMS, seed=0)
     threads = host_threads()
     for _ in range(args.warmup):
-        cpu_reference_run(xyz, radii, threads)
+        cpu_reference_run(xyz, radii, threads, spec)
     times, kind = [], "reference"
     for _ in range(args.steps):
-        dt, _, kind = cpu_reference_run(xyz, radii, threads)
+        dt, _, kind = cpu_reference_run(xyz, radii, threads, spec)
         times.append(dt)
     total = float(np.sum(times))
     value = N_ATOMS * args.steps / total
     emit({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": spec["metric"], "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "atoms": N_ATOMS, "host_threads": threads},
+        "config": shared_config(spec),
+        "details": {"host_threads": threads, "structures": 1,
+                    "note": "the reference is a single-process CPU library: one structure per step at every N"},
         "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": threads, "kind": kind,
                          "sample": "full 100k-atom structure per step, freesasa_calc_coord wall clock"},
         "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,6 +204,112 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# the extra sections of the line (rank 0, after the timed regions)
+# ---------------------------------------------------------------------------------------------------------
+def timed_device(eng, alg, d_xyz, d_rad, res, reps, flush=None, offsets=None):
+    """median integrate-kernel ms and device ms per call over `reps` calls (after one warm-up)."""
+    k, d = [], []
+    for i in range(reps + 1):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        eng.calc_device(alg, d_xyz, d_rad, PROBE, res, offsets=offsets)
+        st = eng.stats()
+        k.append(st["integrate_ms"])
+        d.append(st["device_ms"])
+    return float(np.median(k[1:])), float(np.median(d[1:])), st
+
+
+def section_ablation(fs, eng, spec, d_xyz, d_rad, flush):
+    eng.set_certificate(False)
+    try:
+        k_ms, d_ms, _ = timed_device(eng, spec["alg"], d_xyz, d_rad, spec["resolution"], 3, flush)
+    finally:
+        eng.set_certificate(True)
+    return {"no_certificate": {"value": N_ATOMS / (d_ms * 1e-3), "unit": "atoms/s", "kernel_ms": k_ms, "device_ms": d_ms,
+                               "note": "every atom integrated; results are bit-identical to the certificate-on run (tests/test_certificate.py)"}}
+
+
+def section_surface(fs, eng, spec, dev, torch, flush):
+    """A workload with a protein-like surface fraction: the 1M-atom hollow shell of config C5 on ONE GPU."""
+    from freesasa_b200 import workloads
+
+    x, r = workloads.capsid(1_000_000)
+    dx, dr = torch.tensor(x, device=dev), torch.tensor(r, device=dev)
+    k_ms, d_ms, st = timed_device(eng, spec["alg"], dx, dr, spec["resolution"], 3, flush)
+    return {"workload": "1M-atom hollow shell (config C5's structure), one GPU, device-resident", "atoms": len(r),
+            "value": len(r) / (d_ms * 1e-3), "unit": "atoms/s", "kernel_ms": k_ms, "device_ms": d_ms,
+            "certified_fraction": st["n_certified"] / len(r)}
+
+
+def section_c3(fs, eng, d_xyz, d_rad, xyz, radii, flush, with_oracle):
+    spec = ALGS["sr"]
+    k_ms, d_ms, st = timed_device(eng, spec["alg"], d_xyz, d_rad, spec["resolution"], 5, flush)
+    out = {"workload": spec["workload"], "value": N_ATOMS / (d_ms * 1e-3), "unit": "atoms/s", "kernel_ms": k_ms,
+           "device_ms": d_ms, "certified": st["n_certified"]}
+    if with_oracle:
+        from oracle import bindings as ob
+
+        t = time.perf_counter()
+        e2e = fs.calc_coord(xyz, radii, fs.Parameters(fs.SHRAKE_RUPLEY, PROBE, spec["resolution"], 20, 1)).sasa
+        out["e2e_ms"] = 1e3 * (time.perf_counter() - t)
+        want = ob.oracle_calc(xyz, radii, ob.SHRAKE_RUPLEY, PROBE, spec["resolution"])
+        out["max_abs_dsasa"] = float(np.abs(e2e - want).max())
+        out["tolerance"] = 1e-9
+    return out
+
+
+def section_configs(fs, n_devices, with_oracle):
+    """BASELINE.json configs[3] (C4) and configs[4] (C5) through the C entry point fsb200_calc_multi(): host arrays in,
+    host arrays out, on ONE device and on all `n_devices`; parity against the oracle (C5: every atom; C4: 32 structures)."""
+    from freesasa_b200 import workloads
+
+    out = {}
+    x, r = workloads.capsid(1_000_000)
+    structs = workloads.batch(1024, 4000, 6000, seed=0)
+    n4 = sum(len(b) for _, b in structs)
+    for name, call, atoms in (
+        ("C5", lambda nd: fs.calc_multi(fs.LEE_RICHARDS, [(x, r)], PROBE, 100, nd)[0], len(r)),
+        ("C4", lambda nd: fs.calc_multi(fs.LEE_RICHARDS, structs, PROBE, 50, nd), n4),
+    ):
+        entry = {"atoms": atoms, "entry_point": "fsb200_calc_multi (C ABI, host arrays in / out, one process)"}
+        if name == "C5":
+            entry["workload"] = "C5: one 1M-atom shell, LR n_slices=100; inputs replicated, outputs partitioned (strong scaling)"
+        else:
+            entry["workload"] = "C4: 1024 structures of 4000-6000 atoms, LR n_slices=50, dealt to the GPUs by size (LPT)"
+        got = None
+        for nd in sorted({1, n_devices}):
+            call(nd)  # warm-up: scratch, pinned staging, peer mappings
+            best, stats = None, None
+            for _ in range(3):
+                t = time.perf_counter()
+                got = call(nd)
+                dt = time.perf_counter() - t
+                if best is None or dt < best:
+                    best, stats = dt, fs.multi_stats()
+            e = {"ms": 1e3 * best, "atoms_per_s": atoms / best}
+            if nd > 1:
+                e["stats"] = stats
+            entry[f"gpus_{nd}"] = e
+        if n_devices > 1:
+            entry["speedup"] = entry["gpus_1"]["ms"] / entry[f"gpus_{n_devices}"]["ms"]
+            entry["efficiency_vs_own_1gpu"] = entry["speedup"] / n_devices
+        if with_oracle:
+            from oracle import bindings as ob
+
+            if name == "C5":
+                want = ob.oracle_calc(x, r, ob.LEE_RICHARDS, PROBE, 100)
+                entry["max_abs_dsasa"] = float(np.abs(got - want).max())
+            else:
+                errs = [float(np.abs(got[k] - ob.oracle_calc(structs[k][0], structs[k][1], ob.LEE_RICHARDS, PROBE, 50)).max())
+                        for k in range(0, 1024, 32)]
+                entry["max_abs_dsasa"] = max(errs)
+                entry["structures_checked"] = len(errs)
+            entry["tolerance"] = 1e-3
+        out[name] = entry
+    return out
+
+
 def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
@@ -185,25 +317,30 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--alg", default="lr", choices=["lr", "sr"], help="lr: config C2 (the headline metric); sr: config C3")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = all-gather fused into the kernel (peer stores over NVLink + flag barriers); nccl = ncclAllGather queued behind the kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip ablation / surface workload / C3 / C4 / C5 sections")
     ap.add_argument("--no-certificate", action="store_true",
                     help="ablation: integrate every atom, do not use the buried-atom certificate (results are identical)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    spec = ALGS[args.alg]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, spec)
         return
 
     import torch
     import torch.distributed as dist
 
     import freesasa_b200 as fs
-    from freesasa_b200 import workloads
+    from freesasa_b200 import parallel, workloads
 
     if not fs.available():
         raise SystemExit("bench.py: the CUDA engine is not built or no B200 is visible (there is no CPU fallback)")
@@ -216,12 +353,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: one structure per rank ------------------------------------------------------------
+    alg, res = spec["alg"], spec["resolution"]
     xyz, radii = workloads.globule(N_ATOMS, seed=rank)
     h_xyz = torch.from_numpy(xyz).pin_memory()
     h_rad = torch.from_numpy(radii).pin_memory()
     d_xyz, d_rad = h_xyz.to(dev), h_rad.to(dev)
-    d_out = torch.zeros(N_ATOMS, dtype=torch.float64, device=dev)
-    d_all = torch.zeros(world * N_ATOMS, dtype=torch.float64, device=dev) if distributed else None
     h_all = torch.empty(world * N_ATOMS, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     align = torch.zeros(1, device=dev)
@@ -231,19 +367,46 @@ def main():
     stream = torch.cuda.Stream(dev)  # a real (non-legacy) stream: the engine replays its launch sequence as a CUDA graph on it
     torch.cuda.set_stream(stream)
 
+    collective = "none (N=1)"
+    pg = None
+    if distributed and args.collective == "peer":
+        try:
+            pg = parallel.PeerGather(eng, world * N_ATOMS, rank, world, slot=(rank * N_ATOMS, N_ATOMS))
+            collective = ("fused: areas stored into every rank's symmetric buffer from the kernel epilogue (NVLink peer stores, "
+                          "CUDA IPC), two one-warp flag barriers per step; no NCCL call, one host synchronisation per step")
+        except Exception as e:  # no P2P between the visible devices: the plain variant
+            print(f"bench.py: peer-store all-gather unavailable ({e}); using NCCL", file=sys.stderr)
+            pg = None
+    if distributed and pg is None:
+        d_all = torch.zeros(world * N_ATOMS, dtype=torch.float64, device=dev)
+        d_out = d_all[rank * N_ATOMS:(rank + 1) * N_ATOMS]
+        collective = "kernels enqueued, ONE ncclAllGather (in place) queued behind them, one host synchronisation per step"
+    elif not distributed:
+        d_all = torch.zeros(N_ATOMS, dtype=torch.float64, device=dev)
+        d_out = d_all
+    else:
+        d_all = pg.out
+
     def device_step():
-        eng.calc_device(fs.LEE_RICHARDS, d_xyz, d_rad, PROBE, N_SLICES, out=d_out)
-        if distributed:
-            dist.all_gather_into_tensor(d_all, d_out)
+        if not distributed:
+            eng.calc_device(alg, d_xyz, d_rad, PROBE, res, out=d_out)
+        elif pg is not None:
+            pg.step(lambda out: eng.calc_device_async(alg, d_xyz, d_rad, PROBE, res, out=out))
+        else:
+            parallel.gather_after_enqueue(eng, lambda: eng.calc_device_async(alg, d_xyz, d_rad, PROBE, res, out=d_out),
+                                          lambda local: dist.all_gather_into_tensor(d_all, local) or d_all)
 
     def e2e_step():
         if not distributed:
-            p = fs.Parameters(fs.LEE_RICHARDS, PROBE, 100, N_SLICES, 1)
+            p = fs.Parameters(alg, PROBE, res, res, 1)
             return fs.calc_coord(xyz, radii, p).sasa  # host arrays in, host array out (the drop-in call)
         d_xyz.copy_(h_xyz, non_blocking=True)
         d_rad.copy_(h_rad, non_blocking=True)
         device_step()
-        h_all.copy_(d_all, non_blocking=True)
+        if rank == 0:
+            h_all.copy_(d_all, non_blocking=True)           # the gathered result, once
+        else:
+            h_all[rank * N_ATOMS:(rank + 1) * N_ATOMS].copy_(d_all[rank * N_ATOMS:(rank + 1) * N_ATOMS], non_blocking=True)
         torch.cuda.synchronize(dev)
         return h_all
 
@@ -263,13 +426,14 @@ def main():
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     integrate_ms, device_ms = [], []
     launches0 = fs.launch_count()
+    certified = 0
     with ClockSampler(local_rank) as clocks:
         barrier()
         for k in range(args.steps):
             flush.fill_(k & 0xFF)  # evict L2 between timed steps (outside the timed events)
             if distributed:
-                dist.all_reduce(align)  # ranks leave the (untimed) flush together: the step's all-gather then
-                # only waits for differences in compute time, not for flush/launch skew between ranks
+                dist.all_reduce(align)  # ranks leave the (untimed) flush together: the step then only waits for
+                # differences in compute time, not for flush/launch skew between ranks
             ev0[k].record(stream)
             device_step()
             ev1[k].record(stream)
@@ -291,7 +455,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = e2e_step()
+        res_e2e = e2e_step()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if distributed:
@@ -299,57 +463,97 @@ def main():
     e2e_value = world * N_ATOMS * e2e_steps / float(e2e_s.item())
 
     if rank == 0:
-        got = np.asarray(res[:N_ATOMS]) if distributed else res
+        got = np.asarray(res_e2e[:N_ATOMS]) if distributed else res_e2e
         peak, peak_src = measured_peak_hbm()
         k_ms = float(np.mean(integrate_ms))
         achieved = ALG_BYTES_PER_ATOM * N_ATOMS / (k_ms * 1e-3) / 1e9
+        clk = clocks.summary()
+        ncu = NCU[args.alg]
         line = {
-            "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+            "metric": spec["metric"], "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "atoms_per_gpu": N_ATOMS, "structures": world,
-                       "buried_atom_certificate": ("off (ablation)" if args.no_certificate else
-                                                   f"on: {certified} of {N_ATOMS} atoms proved fully buried, not integrated (exact, DESIGN.md)"),
-                       "l2": "flushed between timed steps (256 MiB device write, outside the events)",
-                       "timing": "CUDA events on the launching stream, sum over steps, max over ranks",
-                       "collective": "one NCCL all-gather of per-atom SASA per step" if distributed else "none (N=1)"},
-            "clocks": clocks.summary(),
+            "config": shared_config(spec),
+            "details": {"structures": world,
+                        "buried_atom_certificate": ("off (ablation)" if args.no_certificate else
+                                                    f"on: {certified} of {N_ATOMS} atoms proved fully buried, not integrated (exact, DESIGN.md)"),
+                        "l2": "flushed between timed steps (256 MiB device write, outside the events)",
+                        "timing": "CUDA events on the launching stream, sum over steps, max over ranks",
+                        "collective": collective},
+            "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": 32 * N_ATOMS * world,
-                    "d2h_bytes_per_step": 8 * N_ATOMS * world * (world if distributed else 1), "steps": e2e_steps,
+                    "d2h_bytes_per_step": 8 * N_ATOMS * (world + (world - 1) if distributed else 1), "steps": e2e_steps,
                     "path": "freesasa_calc_coord() of the C host layer, pageable host arrays" if not distributed
-                    else "pinned host -> H2D -> calc_device -> NCCL all-gather -> D2H on every rank"},
+                    else "pinned host -> H2D -> calc_device_async + fused all-gather -> D2H (rank 0: all ranks' areas; others: their own)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_integrate<LR,float>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, " + NCU_SOURCE + ")",
+            "roofline": {"bound": "fp32-issue", "kernel": spec["kernel"], "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu["dram_bytes_per_launch"],
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture)",
+                         "traffic_source": ncu["source"],
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_ATOM * N_ATOMS, "peak_source": peak_src,
                          "algorithmic_bytes_per_atom": ALG_BYTES_PER_ATOM, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (total_ms / args.steps),
-                         "note": "FP32-issue bound kernel; HBM fraction is tiny by construction (DESIGN.md)"},
+                         "note": "achieved/peak/frac are the HBM figures the contract asks for; the kernel is bound by FP32/ALU "
+                                 "instruction issue (DRAM throughput < 1 %), so `issue` is the fraction that measures it"},
             "device_ms_per_call": float(np.mean(device_ms)),
         }
-        if not args.no_cpu_baseline:
+        if ncu["warp_instructions_per_launch"] and clk.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            slots = sms * 4 * clk["sm_mhz"] * 1e6 * (k_ms * 1e-3)
+            line["roofline"]["issue"] = {"warp_instructions_per_launch": ncu["warp_instructions_per_launch"],
+                                         "issue_slots_per_launch": slots, "frac": ncu["warp_instructions_per_launch"] / slots,
+                                         "how": "warp instructions of the committed ncu capture / (kernel_ms x SMs x 4 schedulers x SM clock sampled in this run)",
+                                         "source": ncu["source"]}
+        with_oracle = not args.no_cpu_baseline
+        if with_oracle:
             threads = host_threads()
-            cpu_s, want, kind = cpu_reference_run(xyz, radii, threads)
+            cpu_s, want, kind = cpu_reference_run(xyz, radii, threads, spec)
             err = np.abs(got - want)
             line["cpu_baseline"] = {"value": N_ATOMS / cpu_s, "unit": "atoms/s", "cores": threads, "kind": kind,
                                     "sample": "the full 100k-atom structure of rank 0, one pass, wall clock around freesasa_calc_coord"}
-            line["parity"] = {"max_abs_dsasa": float(err.max()), "worst_atom": int(err.argmax()), "tolerance": 1e-3,
+            line["parity"] = {"max_abs_dsasa": float(err.max()), "worst_atom": int(err.argmax()),
+                              "tolerance": 1e-3 if args.alg == "lr" else 1e-9,
                               "total_gpu": float(got.sum()), "total_ref": float(want.sum())}
-            nn_pairs = None
+        if args.alg == "lr":
+            try:  # executed vs effective pair-slice rates: the certificate skips most evaluations the reference performs
+                counts = eng.neighbour_counts(xyz, radii, PROBE)
+                integrated = eng.last_certified == 0
+                pairs_all, pairs_exec = int(counts.sum()), int(counts[integrated].sum())
+                line["roofline"]["compute"] = {
+                    "effective_pair_slice_evals_per_s": pairs_all * res / (k_ms * 1e-3),
+                    "executed_pair_slice_evals_per_s": pairs_exec * res / (k_ms * 1e-3),
+                    "effective_pair_slice_evals": pairs_all * res, "executed_pair_slice_evals": pairs_exec * res,
+                    "atoms_integrated": int(integrated.sum()),
+                    "note": "effective = what the reference evaluates for the same answer (sum over ALL atoms of neighbours x slices); "
+                            "executed = the same sum over the atoms this engine actually integrates (the others are proved buried)"}
+            except Exception as e:
+                line["roofline"]["compute"] = {"error": str(e)}
+        if world == 1 and not args.no_extras and not args.no_certificate:
+            torch.cuda.synchronize(dev)
             try:
-                from oracle import bindings as ob
-
-                start, _ = ob.oracle_neighbours(xyz, radii + PROBE)
-                nn_pairs = int(start[-1])
-            except Exception:
-                pass
-            if nn_pairs:
-                line["roofline"]["compute"] = {"pair_slice_evals_per_s": nn_pairs * N_SLICES / (k_ms * 1e-3),
-                                               "pair_slice_evals": nn_pairs * N_SLICES}
-        emit(line)
+                line["ablation"] = section_ablation(fs, eng, spec, d_xyz, d_rad, flush)
+                line["surface_workload"] = section_surface(fs, eng, spec, dev, torch, flush)
+                if args.alg == "lr":
+                    line["c3"] = section_c3(fs, eng, d_xyz, d_rad, xyz, radii, flush, with_oracle)
+            except Exception as e:
+                line["extras_error"] = repr(e)
+        emit_line = line
     if distributed:
         dist.barrier()
+    # ---- configs C4 / C5 through the multi-GPU C entry point: rank 0 drives ALL visible GPUs, the other ranks are idle ----
+    if rank == 0:
+        if not args.no_extras and not args.no_certificate and args.alg == "lr":
+            try:
+                del flush
+                torch.cuda.empty_cache()
+                emit_line["configs"] = section_configs(fs, min(world, fs.device_count()), not args.no_cpu_baseline)
+            except Exception as e:
+                emit_line["configs_error"] = repr(e)
+        emit(emit_line)
+    if distributed:
+        dist.barrier()
+        if pg is not None:
+            pg.close()
         dist.destroy_process_group()
 
 

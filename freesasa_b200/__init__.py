@@ -31,11 +31,14 @@ from . import workloads  # noqa: F401  (numpy-only synthetic inputs)
 
 __all__ = [
     "LEE_RICHARDS", "SHRAKE_RUPLEY", "FP32", "FP64", "Parameters", "Result", "Engine", "Stats",
-    "available", "calc_batch", "calc_coord", "calc_coord_batch", "default_parameters", "library_paths", "workloads",
+    "available", "calc_batch", "calc_coord", "calc_coord_batch", "calc_multi", "default_parameters", "device_count",
+    "library_paths", "multi_stats", "trim", "workloads", "IpcBuffer", "MultiStats",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "csrc", "libfsb200.so")
+# FSB200_ENGINE_LIB: experiment hook of tests/tools/ab_variants.py (a variant build of the same sources); the host layer
+# always links the product library.
+_LIB_PATH = os.environ.get("FSB200_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libfsb200.so")
 _HOST_PATH = os.path.join(_HERE, "csrc", "libfreesasa_b200_host.so")
 
 LEE_RICHARDS = 0  # enum freesasa_algorithm (reference src/freesasa.h:89-92)
@@ -82,6 +85,26 @@ class Stats(ctypes.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+MAX_DEVICES = 16  # FSB200_MAX_DEVICES
+SECOND_PASS = 1   # FSB200_SECOND_PASS
+
+
+class MultiStats(ctypes.Structure):
+    """struct fsb200_multi_stats (include/fsb200.h)."""
+
+    _fields_ = [
+        ("n_devices", ctypes.c_int), ("n_atoms", ctypes.c_int), ("n_structures", ctypes.c_int), ("n_certified", ctypes.c_int),
+        ("upload_ms", ctypes.c_float), ("compute_ms", ctypes.c_float), ("download_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+        ("integrate_ms", ctypes.c_float * MAX_DEVICES), ("device_ms", ctypes.c_float * MAX_DEVICES),
+    ]
+
+    def as_dict(self):
+        n = self.n_devices
+        return {"n_devices": n, "n_atoms": self.n_atoms, "n_structures": self.n_structures, "upload_ms": self.upload_ms,
+                "compute_ms": self.compute_ms, "download_ms": self.download_ms, "total_ms": self.total_ms,
+                "integrate_ms": list(self.integrate_ms)[:n], "device_ms": list(self.device_ms)[:n]}
 
 
 class Result:
@@ -138,6 +161,20 @@ def _engine_lib():
         L.fsb200_sr.argtypes = [_dp, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_int]
         L.fsb200_ctx_calc_device.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, _ip, ctypes.c_double,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+        L.fsb200_ctx_calc_device_async.argtypes = L.fsb200_ctx_calc_device.argtypes
+        L.fsb200_ctx_finish.argtypes = [vp]
+        L.fsb200_ctx_set_peer_outputs.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
+        L.fsb200_ctx_peer_barrier.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), vp]
+        L.fsb200_ctx_peer_barrier_status.argtypes = [vp]
+        L.fsb200_ctx_generation.restype = ctypes.c_ulonglong
+        L.fsb200_ctx_generation.argtypes = [vp]
+        L.fsb200_ipc_alloc.argtypes = [ctypes.c_int, ctypes.c_ulonglong, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.fsb200_ipc_open.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.fsb200_ipc_close.argtypes = [ctypes.c_int, vp]
+        L.fsb200_ipc_free.argtypes = [ctypes.c_int, vp]
+        L.fsb200_calc_multi.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _dpp, _dpp, _dpp, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.fsb200_get_multi_stats.argtypes = [ctypes.POINTER(MultiStats)]
+        L.fsb200_trim.argtypes = []
         L.fsb200_ctx_unpermute.argtypes = [vp, vp, vp, ctypes.c_int, vp]
         L.fsb200_ctx_neighbour_counts.argtypes = [vp, _ip, _dp, _dp, ctypes.c_int, ctypes.c_double]
         for f in ("fsb200_shard_begin", "fsb200_shard_end"):
@@ -256,6 +293,80 @@ def calc_batch(alg: int, structures: Sequence, probe: float = 1.4, resolution: i
     return outs
 
 
+def calc_multi(alg: int, structures: Sequence, probe: float = 1.4, resolution: int = 20, n_devices: int = 0):
+    """fsb200_calc_multi() of the C ABI: one process, several GPUs.  One structure: inputs replicated, outputs partitioned
+    over the devices; several structures: dealt to the devices by size.  Returns the per-atom SASA arrays."""
+    L = _engine_lib()
+    rad = [_f64(r) for _, r in structures]
+    xyz = [_f64(x, 3 * r.shape[0]) for (x, _), r in zip(structures, rad)]
+    outs = [np.empty(r.shape[0], dtype=np.float64) for r in rad]
+    counts = (ctypes.c_int * len(rad))(*[int(r.shape[0]) for r in rad])
+    if L.fsb200_calc_multi(int(alg), len(rad), counts, _ptr_array(xyz), _ptr_array(rad), _ptr_array(outs), float(probe),
+                           int(resolution), int(n_devices)) != 0:
+        raise RuntimeError("fsb200_calc_multi failed: " + _last_error())
+    return outs
+
+
+def multi_stats() -> dict:
+    s = MultiStats()
+    _engine_lib().fsb200_get_multi_stats(ctypes.byref(s))
+    return s.as_dict()
+
+
+def device_count() -> int:
+    return int(_engine_lib().fsb200_device_count())
+
+
+def trim() -> int:
+    """fsb200_trim(): destroy every idle pooled context (device scratch + pinned staging)."""
+    return int(_engine_lib().fsb200_trim())
+
+
+class IpcBuffer:
+    """A device buffer other processes can map (CUDA IPC): the symmetric output / flag buffers of the fused all-gather.
+    ``handle`` (64 bytes) is what a peer passes to ``IpcBuffer.open``."""
+
+    def __init__(self, device: int, nbytes: int, _ptr=None, _handle=None, _owner=True):
+        L = _engine_lib()
+        self.device, self.nbytes, self._owner = int(device), int(nbytes), _owner
+        if _ptr is None:
+            p, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            if L.fsb200_ipc_alloc(self.device, self.nbytes, ctypes.byref(p), h) != 0:
+                raise RuntimeError("fsb200_ipc_alloc failed: " + _last_error())
+            self.ptr, self.handle = p.value, h.raw
+        else:
+            self.ptr, self.handle = _ptr, _handle
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, nbytes: int):
+        p = ctypes.c_void_p()
+        if _engine_lib().fsb200_ipc_open(int(device), handle, ctypes.byref(p)) != 0:
+            raise RuntimeError("fsb200_ipc_open failed: " + _last_error())
+        return cls(device, nbytes, _ptr=p.value, _handle=handle, _owner=False)
+
+    def tensor(self, dtype, count):
+        """torch view of the buffer (no copy) on this process's device."""
+        import torch
+
+        class _Iface:
+            pass
+
+        it = _Iface()
+        itemsize = torch.tensor([], dtype=dtype).element_size()
+        typestr = {torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+        it.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(self.ptr), False), "version": 2}
+        assert count * itemsize <= self.nbytes
+        t = torch.as_tensor(it, device=torch.device("cuda", self.device))
+        t._fsb200_keepalive = self
+        return t
+
+    def close(self):
+        if self.ptr:
+            L = _engine_lib()
+            (L.fsb200_ipc_free if self._owner else L.fsb200_ipc_close)(self.device, ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
 # ------------------------------------------------------------------------------------------------------
 # engine-level access (explicit context)
 # ------------------------------------------------------------------------------------------------------
@@ -350,6 +461,55 @@ class Engine:
                                                    off_p, float(probe), int(resolution), int(shard[0]), int(shard[1]),
                                                    out.data_ptr(), ctypes.c_void_p(stream)), "fsb200_ctx_calc_device")
         return out
+
+    def calc_device_async(self, alg: int, d_xyz, d_radii, probe: float = 1.4, resolution: int = 20, offsets=None,
+                          shard=(0, 1), out=None, stream=None):
+        """First half of calc_device: validates and enqueues, does not wait.  Queue a collective on the same stream, then
+        call finish()."""
+        import torch
+
+        assert d_xyz.is_cuda and d_radii.is_cuda and d_xyz.dtype == torch.float64 and d_radii.dtype == torch.float64
+        assert d_xyz.is_contiguous() and d_radii.is_contiguous()
+        n = int(d_radii.shape[0])
+        if out is None:
+            out = torch.zeros(n, dtype=torch.float64, device=d_radii.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_radii.device).cuda_stream
+        n_struct, off_p = 1, None
+        if offsets is not None:
+            off = np.ascontiguousarray(offsets, dtype=np.int32)
+            n_struct, off_p = int(off.shape[0]) - 1, off.ctypes.data_as(_ip)
+        self._check(self._L.fsb200_ctx_calc_device_async(self._ctx, int(alg), d_xyz.data_ptr(), d_radii.data_ptr(), n, n_struct,
+                                                         off_p, float(probe), int(resolution), int(shard[0]), int(shard[1]),
+                                                         out.data_ptr(), ctypes.c_void_p(stream)), "fsb200_ctx_calc_device_async")
+        return out
+
+    def finish(self) -> int:
+        """Second half: the one synchronisation.  Returns 0, or SECOND_PASS (work queued in between must be redone)."""
+        rc = self._L.fsb200_ctx_finish(self._ctx)
+        if rc not in (0, SECOND_PASS):
+            raise RuntimeError("fsb200_ctx_finish failed: " + _last_error())
+        return rc
+
+    def set_peer_outputs(self, pointers: Sequence[int]):
+        """Mirror every area into these device buffers (usually on other GPUs) from the kernel epilogue."""
+        arr = (ctypes.c_void_p * max(1, len(pointers)))(*[ctypes.c_void_p(int(p)) for p in pointers])
+        self._check(self._L.fsb200_ctx_set_peer_outputs(self._ctx, len(pointers), arr), "fsb200_ctx_set_peer_outputs")
+
+    def peer_barrier(self, rank: int, world: int, flag_pointers: Sequence[int], stream=None):
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in flag_pointers])
+        self._check(self._L.fsb200_ctx_peer_barrier(self._ctx, int(rank), int(world), arr, ctypes.c_void_p(stream)),
+                    "fsb200_ctx_peer_barrier")
+
+    def peer_barrier_status(self):
+        self._check(self._L.fsb200_ctx_peer_barrier_status(self._ctx), "fsb200_ctx_peer_barrier_status")
+
+    def generation(self) -> int:
+        return int(self._L.fsb200_ctx_generation(self._ctx))
 
     def unpermute(self, d_sorted, out=None, stream=None):
         import torch

@@ -56,6 +56,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, force: bool = False, replace=None) -> str:
+    """Experiment build: the same sources with extra -D knobs (engine.cuh) -> csrc/libfsb200_<name>.so, used by
+    tests/tools/ab_variants.py to measure one change at a time on the GPU box (FSB200_ENGINE_LIB selects it).
+    `replace` maps a source name to another file (e.g. an older revision of integrate.cu taken from git)."""
+    srcs = [(replace or {}).get(s, os.path.join(CSRC, s)) for s in SOURCES]
+    out = os.path.join(CSRC, f"libfsb200_{name}.so")
+    if force or _stale(out, srcs + HEADERS + [os.path.abspath(__file__)]):
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+               "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-I", CSRC, "-o", out, *[f"-D{d}" for d in defines], *srcs]
+        if os.path.exists("/usr/bin/g++"):
+            cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+        subprocess.run(cmd, check=True)
+    return out
+
+
 def build_host_shim(force: bool = False) -> str:
     """The C host layer that mirrors the reference's own entry points (freesasa_calc_coord ...)."""
     srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES]

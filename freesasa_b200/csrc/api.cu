@@ -7,6 +7,8 @@
 #include "../../include/fsb200.h"
 #include "engine.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -17,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -30,6 +33,7 @@ const float kCertDirs[kCertPairs][3] = {
 };
 
 thread_local char g_error[512] = "";
+thread_local fsb200_stats g_last_stats{};   // of the last context-free call on this thread (fsb200_last_stats)
 std::atomic<unsigned long long> g_launches{0};
 
 int fail(const char *fmt, ...)
@@ -39,6 +43,27 @@ int fail(const char *fmt, ...)
     vsnprintf(g_error, sizeof g_error, fmt, ap);
     va_end(ap);
     return FSB200_FAIL;
+}
+
+// NVTX range for one phase of a call (upload / cell build / integrate / download / multi-device)
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
+
+// C++ exceptions must not cross the C ABI (std::bad_alloc from a vector, std::system_error from a thread that cannot be
+// started): every extern "C" entry point that allocates runs its body through this.
+template <typename F> int guarded(F body)
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return fail("out of host memory");
+    } catch (const std::exception &e) {
+        return fail("internal error: %s", e.what());
+    } catch (...) {
+        return fail("internal error: unknown exception");
+    }
 }
 
 #define CU(call)                                                                                   \
@@ -108,6 +133,21 @@ struct fsb200_ctx {
     DevBuf<float4> points_f;
     DevBuf<double> points_d;
     int last_n = 0;  // atoms of the last device call (for unpermute)
+    bool perm_from_device_call = false;   // the permutation in `perm` belongs to the last fsb200_ctx_calc_device[_async] call
+    unsigned long long generation = 0;    // bumped by every pipeline run on this context (stamps `perm`)
+    // a call that has been enqueued (fsb200_ctx_calc_device_async) but not finished (fsb200_ctx_finish)
+    struct Pending {
+        bool active = false;
+        int alg = 0, n = 0, n_struct = 0, launches = 0;
+        cudaStream_t stream = nullptr;
+        Workspace ws;
+        IntegrateArgs ia;
+    } pending;
+    // mirrors of the output on other GPUs (fsb200_ctx_set_peer_outputs), applied to device-resident calls
+    int barrier_epoch = 0;
+    DevBuf<int> barrier_status;   // one int, 0 = fine
+    int n_peer_out = 0;
+    double *peer_out[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -336,13 +376,22 @@ struct Request {
     int *d_nn;             // optional
     int shard_index, shard_count;
     cudaStream_t stream;
+    int sorted_output = 0;   // 1: d_out[sorted position]; 0: d_out[caller index]
+    bool device_call = false;
+    int n_peer_out = 0;
+    double *const *peer_out = nullptr;
 };
 
-// Enqueue the whole pipeline.  `after_enqueue` (may be null) lets the host-buffer entry points queue
-// their result download before the one synchronisation of the call.
-template <typename F>
-int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
+// A call is two halves.  enqueue_pipeline() validates and puts the whole device sequence on the stream — cell-list build
+// (one CUDA graph launch), the persistent integration kernel, the download of the status block — and returns without
+// waiting; the caller may queue more work behind it (its result download, a collective, peer signalling).
+// finish_pipeline() is the ONE synchronisation of the call: it waits, reads the status block, and only in the rare
+// large-neighbourhood case runs the second pass (returning kSecondPass so that work queued in between can be redone).
+constexpr int kSecondPass = 1;
+
+int enqueue_pipeline(fsb200_ctx *c, const Request &rq)
 {
+    if (c->pending.active) return fail("a call is still pending on this context: call fsb200_ctx_finish() first");
     if (rq.alg != FSB200_LEE_RICHARDS && rq.alg != FSB200_SHRAKE_RUPLEY) return fail("unknown algorithm %d", rq.alg);
     if (rq.n <= 0) return fail("no atoms");
     if (rq.resolution <= 0) return fail("invalid resolution %d, must be > 0", rq.resolution);
@@ -356,6 +405,8 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     ws.xyz = rq.d_xyz;
     ws.radii = rq.d_radii;
     ws.probe = rq.probe;
+    ws.shard_begin = fsb200_shard_begin(rq.n, rq.shard_index, rq.shard_count);
+    ws.shard_end = fsb200_shard_end(rq.n, rq.shard_index, rq.shard_count);
     if (rq.n_struct > 1)
         CU(cudaMemcpyAsync(ws.offsets, rq.h_offsets, sizeof(int) * ((size_t)rq.n_struct + 1), cudaMemcpyHostToDevice, st));
 
@@ -364,11 +415,13 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     ia.alg = rq.alg;
     ia.resolution = rq.resolution;
     ia.precision = c->precision;
-    ia.shard_begin = fsb200_shard_begin(rq.n, rq.shard_index, rq.shard_count);
-    ia.shard_end = fsb200_shard_end(rq.n, rq.shard_index, rq.shard_count);
-    ia.sorted_output = rq.shard_count > 1;
+    ia.shard_begin = ws.shard_begin;
+    ia.shard_end = ws.shard_end;
+    ia.sorted_output = rq.sorted_output;
     ia.out = rq.d_out;
     ia.nn_out = rq.d_nn;
+    ia.n_peer_out = rq.n_peer_out;
+    for (int q = 0; q < rq.n_peer_out; ++q) ia.peer_out[q] = rq.peer_out[q];
     if (rq.alg == FSB200_SHRAKE_RUPLEY) {
         if (ensure_points(c, rq.resolution, st)) return FSB200_FAIL;
         ia.points_f = c->points_f.p;
@@ -384,49 +437,78 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     // directly so that plain CUDA events can bracket it (events recorded inside a graph cannot be timed).
     int launches = 0;
     CU(cudaEventRecord(c->ev[0], st));
-    bool replayed = false;
-    if (c->graph_exec && std::memcmp(&c->graph_ws, &ws, sizeof ws) == 0) {
-        replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
-        launches = c->graph_launches;
-    } else if (std::memcmp(&c->last_ws, &ws, sizeof ws) != 0) {
-        // first sighting of this workspace: plain launches; capturing pays off only for repeated shapes
-    } else if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
-               (c->graph_exec ? (cudaGraphExecDestroy(c->graph_exec), c->graph_exec = nullptr, true) : true) &&
-               cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        launches = launch_cell_build(ws, st);
-        cudaGraph_t graph = nullptr;
-        const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
-        if (e_end == cudaSuccess && graph && cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess) {
-            c->graph_ws = ws;
-            c->graph_launches = launches;
+    {
+        Range r("fsb200:cell_build");
+        bool replayed = false;
+        if (c->graph_exec && std::memcmp(&c->graph_ws, &ws, sizeof ws) == 0) {
             replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
-        } else {
-            c->graph_exec = nullptr;
+            launches = c->graph_launches;
+        } else if (std::memcmp(&c->last_ws, &ws, sizeof ws) != 0) {
+            // first sighting of this workspace: plain launches; capturing pays off only for repeated shapes
+        } else if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+                   (c->graph_exec ? (cudaGraphExecDestroy(c->graph_exec), c->graph_exec = nullptr, true) : true) &&
+                   cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            launches = launch_cell_build(ws, st);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+            if (e_end == cudaSuccess && graph && cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess) {
+                c->graph_ws = ws;
+                c->graph_launches = launches;
+                replayed = cudaGraphLaunch(c->graph_exec, st) == cudaSuccess;
+            } else {
+                c->graph_exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
         }
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
+        if (!replayed) launches = launch_cell_build(ws, st);  // plain stream launches (new shape, legacy stream, or capture refused)
+        c->last_ws = ws;
     }
-    if (!replayed) launches = launch_cell_build(ws, st);  // plain stream launches (new shape, legacy stream, or capture refused)
-    c->last_ws = ws;
     CU(cudaEventRecord(c->ev[1], st));
-    launches += launch_integrate(ws, ia, st);
+    {
+        Range r("fsb200:integrate");
+        launches += launch_integrate(ws, ia, st);
+    }
     CU(cudaEventRecord(c->ev[2], st));
     CU(cudaMemcpyAsync(c->h_status, ws.counters, sizeof(int) * kCtrCount, cudaMemcpyDeviceToHost, st));
-    if (after_enqueue(st)) return FSB200_FAIL;
+    CU(cudaGetLastError());
+    fsb200_ctx::Pending &p = c->pending;
+    p.active = true;
+    p.alg = rq.alg;
+    p.n = rq.n;
+    p.n_struct = rq.n_struct;
+    p.launches = launches;
+    p.stream = st;
+    p.ws = ws;
+    p.ia = ia;
+    ++c->generation;
+    c->last_n = rq.n;
+    c->perm_from_device_call = rq.device_call;
+    return FSB200_SUCCESS;
+}
+
+// `after_second_pass(stream)` re-queues whatever the caller had queued behind the first pass (its download).
+template <typename F>
+int finish_pipeline(fsb200_ctx *c, F after_second_pass)
+{
+    fsb200_ctx::Pending &p = c->pending;
+    if (!p.active) return fail("fsb200_ctx_finish: no call is pending on this context");
+    p.active = false;
+    cudaStream_t st = p.stream;
+    int launches = p.launches;
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    c->last_n = rq.n;
 
     fsb200_stats &s = c->stats;
-    s.n_atoms = rq.n;
-    s.n_structures = rq.n_struct;
+    s.n_atoms = p.n;
+    s.n_structures = p.n_struct;
     s.n_items = c->h_status[kCtrItems] + c->h_status[kCtrItemsBack];
     s.n_overflow = c->h_status[kCtrOverflow];
     s.n_certified = c->h_status[kCtrCertified];
     s.max_neighbours = 0;
     if (c->h_status[kCtrBadInput]) {
         g_launches += launches;
-        return fail("non-finite coordinate or radius in input");
+        return fail("non-finite coordinate or radius in input (or a coordinate range that overflows a double)");
     }
     if (c->h_status[kCtrStalled]) {
         g_launches += launches;
@@ -439,34 +521,103 @@ int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
     if (cudaEventElapsedTime(&s.device_ms, c->ev[0], c->ev[2]) != cudaSuccess) s.device_ms = -1.f;
     if (cudaEventElapsedTime(&s.integrate_ms, c->ev[1], c->ev[2]) != cudaSuccess) s.integrate_ms = -1.f;
     cudaGetLastError();
+    int rc = FSB200_SUCCESS;
     if (s.n_overflow > 0) {
         // Large neighbourhoods (more than kNbCap neighbours): second pass with the lists in global memory.
+        Range r("fsb200:overflow_pass");
         const int cap = ((c->h_status[kCtrMaxCand] + 7) / 8) * 8;
         s.max_neighbours = c->h_status[kCtrMaxCand];
         const int warps = overflow_warps(s.n_overflow);
         CU(c->scratch.ensure(overflow_scratch_bytes(warps, cap, c->precision)));
         CU(cudaEventRecord(c->ev[0], st));  // ev[0]/ev[2] of the first pass were consumed above
-        launches += launch_overflow(ws, ia, s.n_overflow, cap, c->scratch.p, st);
+        launches += launch_overflow(p.ws, p.ia, s.n_overflow, cap, c->scratch.p, st);
         CU(cudaEventRecord(c->ev[3], st));
-        if (after_enqueue(st)) return FSB200_FAIL;
+        if (after_second_pass(st)) return FSB200_FAIL;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         cudaEventElapsedTime(&overflow_ms, c->ev[0], c->ev[3]);
+        rc = kSecondPass;
     }
     s.device_ms += overflow_ms;
     s.kernel_launches = launches;
     g_launches += launches;
-    return FSB200_SUCCESS;
+    return rc;
+}
+
+// Both halves back to back.  `after_enqueue` (may do nothing) lets the host-buffer entry points queue their result
+// download before the one synchronisation of the call; it runs again after a second pass.
+template <typename F>
+int run_pipeline(fsb200_ctx *c, const Request &rq, F after_enqueue)
+{
+    if (enqueue_pipeline(c, rq)) return FSB200_FAIL;
+    if (after_enqueue(rq.stream)) {
+        c->pending.active = false;
+        cudaStreamSynchronize(rq.stream);
+        return FSB200_FAIL;
+    }
+    const int rc = finish_pipeline(c, after_enqueue);
+    return rc == kSecondPass ? FSB200_SUCCESS : rc;
+}
+
+// ---- peer barrier over NVLink ---------------------------------------------------------------------------------
+// flags[r] is rank r's flag array (world ints, peer-mapped).  A rank signals by storing the epoch into slot `rank` of EVERY
+// rank's array (st.release.sys: everything this GPU wrote before — the peer stores of the integration kernel that ran
+// earlier on the same stream — is visible to whoever acquires the flag) and then waits until every slot of ITS OWN array
+// has reached the epoch (ld.acquire.sys).  One warp, lane = peer.  The wait is bounded: a dead peer turns into an error
+// code in *status (rank + 1), never into a hung GPU.
+struct PeerFlags {
+    int *flags[kMaxPeers + 1];
+};
+
+__global__ void k_peer_barrier(PeerFlags pf, int rank, int world, int epoch, int *status)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[r] + rank), "r"(epoch) : "memory");
+        const int *mine = pf.flags[rank] + r;
+        bool ok = false;
+        for (long long spin = 0; spin < (1ll << 24); ++spin) {    // >= 3 s with the back-off below
+            int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (v - epoch >= 0) {
+                ok = true;
+                break;
+            }
+            __nanosleep(200);
+        }
+        if (!ok) atomicCAS(status, 0, r + 1);
+    }
 }
 
 // ---- context pool for the context-free entry points ---------------------------------------------------
+// Idle contexts keep their device scratch (that is the point of the pool) but NOT unbounded host memory: a context whose
+// pinned staging buffer grew beyond kPoolStageKeep gives it back when it returns to the pool, at most kPoolMaxIdle idle
+// contexts are kept per device (surplus ones are destroyed), and fsb200_trim() releases everything that is idle.
 std::mutex g_pool_lock;
 std::vector<fsb200_ctx *> g_pool;  // idle contexts (any device)
+constexpr size_t kPoolStageKeep = 256ull << 20;
+constexpr int kPoolMaxIdle = 4;
 
-fsb200_ctx *pool_acquire()
+// FREESASA_B200_DEVICE=<k>: the device the context-free entry points use when the caller has not chosen one with
+// cudaSetDevice (i.e. the thread's current device is 0).
+int default_device()
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev == 0) {
+        static const int env_dev = [] {
+            const char *e = getenv("FREESASA_B200_DEVICE");
+            return e && *e ? atoi(e) : 0;
+        }();
+        if (env_dev > 0) dev = env_dev;
+    }
+    return dev;
+}
+
+fsb200_ctx *pool_acquire(int dev = -1)
+{
+    if (dev < 0) dev = default_device();
+    if (dev < 0) {
         fail("no CUDA device available: %s", cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -484,8 +635,22 @@ fsb200_ctx *pool_acquire()
 
 void pool_release(fsb200_ctx *c)
 {
-    std::lock_guard<std::mutex> g(g_pool_lock);
-    g_pool.push_back(c);
+    if (c->h_stage_cap > kPoolStageKeep) {   // one huge call must not pin gigabytes of host memory for the life of the process
+        cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr;
+        c->h_stage_cap = 0;
+    }
+    c->n_peer_out = 0;
+    {
+        std::lock_guard<std::mutex> g(g_pool_lock);
+        int same = 0;
+        for (fsb200_ctx *o : g_pool) same += o->device == c->device;
+        if (same < kPoolMaxIdle) {
+            g_pool.push_back(c);
+            return;
+        }
+    }
+    fsb200_ctx_destroy(c);
 }
 
 struct DeviceGuard {
@@ -588,7 +753,7 @@ void fsb200_ctx_destroy(fsb200_ctx *c)
     c->offsets.release(); c->cell_of.release(); c->cell_start.release(); c->cell_fill.release();
     c->slot_atom.release(); c->perm.release(); c->scan_tmp.release(); c->counters.release();
     c->overflow.release(); c->bounds.release(); c->grid.release(); c->atoms.release();
-    c->items.release(); c->scratch.release(); c->points_f.release(); c->points_d.release(); c->cert_points.release();
+    c->items.release(); c->scratch.release(); c->barrier_status.release(); c->points_f.release(); c->points_d.release(); c->cert_points.release();
     for (int k = 0; k < 4; ++k)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -741,30 +906,171 @@ int fsb200_ctx_neighbour_counts(fsb200_ctx *c, int *counts, const double *xyz, c
     return run_pipeline(c, rq, download);
 }
 
-int fsb200_ctx_calc_device(fsb200_ctx *c, int alg, const double *d_xyz, const double *d_radii, int n_total, int n_struct,
-                           const int *offsets, double probe, int resolution, int shard_index, int shard_count,
-                           double *d_sasa, void *stream)
+static int device_request(fsb200_ctx *c, Request &rq, int alg, const double *d_xyz, const double *d_radii, int n_total,
+                          int n_struct, const int *offsets, double probe, int resolution, int shard_index, int shard_count,
+                          double *d_sasa, void *stream)
 {
     if (!c || !d_xyz || !d_radii || !d_sasa) return fail("null argument");
     if (n_struct < 1 || (n_struct > 1 && !offsets)) return fail("offsets required for %d structures", n_struct);
     if (n_struct > 1 && shard_count > 1) return fail("sharding applies to a single replicated structure");
     if (n_struct > 1 && (offsets[0] != 0 || offsets[n_struct] != n_total)) return fail("offsets do not span the atoms");
-    std::lock_guard<std::mutex> g(c->lock);
-    DeviceGuard guard(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    Request rq{alg, resolution, probe, n_total, n_struct, offsets, d_xyz, d_radii, d_sasa, nullptr, shard_index, shard_count, st};
-    return run_pipeline(c, rq, [](cudaStream_t) { return FSB200_SUCCESS; });
+    rq = Request{alg, resolution, probe, n_total, n_struct, offsets, d_xyz, d_radii, d_sasa, nullptr, shard_index, shard_count, st};
+    rq.device_call = true;
+    // with mirrors (fsb200_ctx_set_peer_outputs) every buffer receives the caller-order areas of this shard directly;
+    // without, a shard writes its range of the SORTED order (gather the ranges, then fsb200_ctx_unpermute)
+    rq.n_peer_out = c->n_peer_out;
+    rq.peer_out = c->peer_out;
+    rq.sorted_output = (shard_count > 1 && c->n_peer_out == 0) ? 1 : 0;
+    return FSB200_SUCCESS;
 }
+
+int fsb200_ctx_calc_device(fsb200_ctx *c, int alg, const double *d_xyz, const double *d_radii, int n_total, int n_struct,
+                           const int *offsets, double probe, int resolution, int shard_index, int shard_count,
+                           double *d_sasa, void *stream)
+{
+    return guarded([&]() -> int {
+        Request rq{};
+        if (device_request(c, rq, alg, d_xyz, d_radii, n_total, n_struct, offsets, probe, resolution, shard_index, shard_count, d_sasa, stream))
+            return FSB200_FAIL;
+        std::lock_guard<std::mutex> g(c->lock);
+        DeviceGuard guard(c->device);
+        return run_pipeline(c, rq, [](cudaStream_t) { return FSB200_SUCCESS; });
+    });
+}
+
+int fsb200_ctx_calc_device_async(fsb200_ctx *c, int alg, const double *d_xyz, const double *d_radii, int n_total, int n_struct,
+                                 const int *offsets, double probe, int resolution, int shard_index, int shard_count,
+                                 double *d_sasa, void *stream)
+{
+    return guarded([&]() -> int {
+        Request rq{};
+        if (device_request(c, rq, alg, d_xyz, d_radii, n_total, n_struct, offsets, probe, resolution, shard_index, shard_count, d_sasa, stream))
+            return FSB200_FAIL;
+        std::lock_guard<std::mutex> g(c->lock);
+        DeviceGuard guard(c->device);
+        return enqueue_pipeline(c, rq);
+    });
+}
+
+int fsb200_ctx_finish(fsb200_ctx *c)
+{
+    if (!c) return fail("null context");
+    return guarded([&]() -> int {
+        std::lock_guard<std::mutex> g(c->lock);
+        DeviceGuard guard(c->device);
+        return finish_pipeline(c, [](cudaStream_t) { return FSB200_SUCCESS; });
+    });
+}
+
+int fsb200_ctx_set_peer_outputs(fsb200_ctx *c, int n_peers, double *const *d_peer_sasa)
+{
+    if (!c) return fail("null context");
+    if (n_peers < 0 || n_peers > kMaxPeers) return fail("at most %d peer outputs", kMaxPeers);
+    if (n_peers > 0 && !d_peer_sasa) return fail("null peer array");
+    std::lock_guard<std::mutex> g(c->lock);
+    if (c->pending.active) return fail("a call is still pending on this context");
+    for (int q = 0; q < n_peers; ++q) {
+        if (!d_peer_sasa[q]) return fail("peer output %d is null", q);
+        c->peer_out[q] = d_peer_sasa[q];
+    }
+    c->n_peer_out = n_peers;
+    return FSB200_SUCCESS;
+}
+
+unsigned long long fsb200_ctx_generation(const fsb200_ctx *c) { return c ? c->generation : 0ull; }
 
 int fsb200_ctx_unpermute(fsb200_ctx *c, const double *d_sorted, double *d_out, int n_total, void *stream)
 {
     if (!c || !d_sorted || !d_out) return fail("null argument");
-    if (n_total != c->last_n) return fail("unpermute: %d atoms but the last call had %d", n_total, c->last_n);
     std::lock_guard<std::mutex> g(c->lock);
+    // `perm` is that of the LAST pipeline run on this context: refuse if that was not a device-resident call of this size
+    // (a host-pointer call or fsb200_ctx_neighbour_counts in between silently replaces the permutation)
+    if (c->pending.active) return fail("unpermute: a call is still pending on this context (fsb200_ctx_finish first)");
+    if (!c->perm_from_device_call) return fail("unpermute: the last call on this context was not fsb200_ctx_calc_device");
+    if (n_total != c->last_n) return fail("unpermute: %d atoms but the last call had %d", n_total, c->last_n);
     DeviceGuard guard(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     g_launches += launch_unpermute(c->perm.p, d_sorted, d_out, n_total, st);
     CU(cudaStreamSynchronize(st));
+    return FSB200_SUCCESS;
+}
+
+// ---- CUDA IPC + peer barrier: the one-process-per-GPU form of the fused all-gather -------------------------------
+int fsb200_ipc_alloc(int device, unsigned long long bytes, void **d_ptr, unsigned char handle[64])
+{
+    if (!d_ptr || !handle || bytes == 0) return fail("invalid arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DeviceGuard guard(device);
+    void *p = nullptr;
+    CU(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        cudaFree(p);
+        return fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaDeviceSynchronize());
+    std::memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ipc_open(int device, const unsigned char handle[64], void **d_ptr)
+{
+    if (!d_ptr || !handle) return fail("invalid arguments");
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ipc_close(int device, void *d_ptr)
+{
+    DeviceGuard guard(device);
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ipc_free(int device, void *d_ptr)
+{
+    DeviceGuard guard(device);
+    CU(cudaFree(d_ptr));
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ctx_peer_barrier(fsb200_ctx *c, int rank, int world, int *const *d_flags, void *stream)
+{
+    if (!c || !d_flags) return fail("null argument");
+    if (world < 1 || world > kMaxPeers + 1 || rank < 0 || rank >= world) return fail("invalid rank %d of %d", rank, world);
+    std::lock_guard<std::mutex> g(c->lock);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    PeerFlags pf;
+    for (int r = 0; r < world; ++r) {
+        if (!d_flags[r]) return fail("flag array of rank %d is null", r);
+        pf.flags[r] = d_flags[r];
+    }
+    const int epoch = ++c->barrier_epoch;
+    if (!c->barrier_status.p) {
+        CU(c->barrier_status.ensure(1));
+        CU(cudaMemsetAsync(c->barrier_status.p, 0, sizeof(int), st));
+    }
+    k_peer_barrier<<<1, 32, 0, st>>>(pf, rank, world, epoch, c->barrier_status.p);
+    g_launches += 1;
+    CU(cudaGetLastError());
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ctx_peer_barrier_status(fsb200_ctx *c)
+{
+    if (!c) return fail("null context");
+    std::lock_guard<std::mutex> g(c->lock);
+    DeviceGuard guard(c->device);
+    int status = 0;
+    CU(cudaMemcpy(&status, c->barrier_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status != 0) return fail("peer barrier timed out waiting for rank %d (a peer died or never reached the barrier)", status - 1);
     return FSB200_SUCCESS;
 }
 
@@ -808,6 +1114,7 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
         fsb200_ctx *c = pool_acquire();
         if (!c) return FSB200_FAIL;
         const int rc = fsb200_ctx_calc_batch(c, alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
+        g_last_stats = c->stats;
         pool_release(c);
         return rc;
     }
@@ -852,10 +1159,348 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
     for (int w = 1; w < n_workers; ++w) helpers.emplace_back(work, w);
     work(0);
     for (auto &h : helpers) h.join();
+    g_last_stats = ctx[0]->stats;   // the last sub-batch of worker 0; totals below
+    g_last_stats.n_atoms = (int)total;
+    g_last_stats.n_structures = n_struct;
     for (int w = 0; w < n_workers; ++w) pool_release(ctx[w]);
     for (int w = 0; w < n_workers; ++w)
         if (rc[w] != FSB200_SUCCESS) return fail("%.500s", err[w]);
     return FSB200_SUCCESS;
+}
+
+// ---- several GPUs behind one C call --------------------------------------------------------------------------
+// One host thread per device, one pooled context each; no NCCL (one process): the exchange steps are peer copies and
+// peer stores over NVLink.
+//   * n_struct == 1 (one huge structure, config C5): the inputs are REPLICATED, the outputs PARTITIONED.  Device d
+//     uploads only its 1/N slice of xyz / radii over its own PCIe link, then every device pulls the other slices from
+//     its peers (an all-gather of the inputs over NVLink, N-1 peer copies per device); every device builds the identical
+//     deterministic cell list, integrates only its contiguous share of the cell-sorted order, and stores each area
+//     straight into device 0's result buffer in the caller's order (peer store from the integration epilogue: the
+//     all-gather of the outputs costs no launch and no extra pass); device 0 downloads the result.
+//     Every atom sees ALL its neighbours — this is the whole-structure SASA, not the per-chain quantity of the
+//     reference's --separate-chains (src/structure.c:955-1081).
+//   * n_struct > 1 (independent structures, config C4): structures are dealt to the devices by longest-processing-time
+//     on their atom counts; every device runs fsb200_calc_batch() on its share (uploads / downloads overlapped with the
+//     kernels on two contexts), results land directly in the caller's per-structure arrays.
+namespace {
+
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n, count = 0, generation = 0;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void drop()   // a participant that could not be started
+    {
+        std::unique_lock<std::mutex> lk(m);
+        if (--n > 0 && count == n) {
+            count = 0;
+            ++generation;
+            cv.notify_all();
+        }
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = generation;
+        if (++count >= n) {
+            count = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != g; });
+        }
+    }
+};
+
+fsb200_multi_stats g_multi_stats{};
+std::mutex g_multi_stats_lock;
+
+bool enable_peer(int from, int to)
+{
+    DeviceGuard guard(from);
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, from, to) != cudaSuccess || !can) {
+        cudaGetLastError();
+        return false;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    cudaGetLastError();
+    return e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+}
+
+double ms_since(std::chrono::steady_clock::time_point t0)
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int multi_replicated(int alg, int n, const double *xyz, const double *radii, double *sasa, double probe, int resolution,
+                     const std::vector<int> &devs)
+{
+    const int N = (int)devs.size();
+    for (int a = 0; a < N; ++a)
+        for (int b = 0; b < N; ++b)
+            if (a != b && !enable_peer(devs[a], devs[b]))
+                return fail("fsb200_calc_multi: devices %d and %d cannot access each other's memory (no NVLink / PCIe P2P)", devs[a], devs[b]);
+    std::vector<fsb200_ctx *> ctx(N, nullptr);
+    for (int d = 0; d < N; ++d) {
+        ctx[d] = pool_acquire(devs[d]);
+        if (!ctx[d]) {
+            for (int e = 0; e < d; ++e) pool_release(ctx[e]);
+            return FSB200_FAIL;
+        }
+    }
+    std::vector<cudaEvent_t> uploaded(N, nullptr);
+    std::vector<int> rc(N, FSB200_SUCCESS);
+    std::vector<std::string> err(N);
+    std::atomic<bool> failed{false};
+    HostBarrier barrier(N);
+    fsb200_multi_stats ms{};
+    ms.n_devices = N;
+    ms.n_atoms = n;
+    ms.n_structures = 1;
+    const auto t_begin = std::chrono::steady_clock::now();
+
+    auto work = [&](int d) {
+        fsb200_ctx *c = ctx[d];
+        std::lock_guard<std::mutex> lock(c->lock);
+        cudaSetDevice(c->device);
+        cudaStream_t st = c->stream;
+        auto check = [&](int r) {
+            if (r != FSB200_SUCCESS && rc[d] == FSB200_SUCCESS) {
+                rc[d] = r;
+                err[d] = g_error;
+                failed.store(true);
+            }
+        };
+        auto cu = [&](cudaError_t e, const char *what) {
+            if (e != cudaSuccess) check(fail("%s failed on device %d: %s", what, c->device, cudaGetErrorString(e)));
+        };
+        const int a0 = fsb200_shard_begin(n, d, N), a1 = fsb200_shard_end(n, d, N), cnt = a1 - a0;
+        {   // phase 1: my slice of the inputs, pageable -> my pinned staging -> my device, over my own PCIe link
+            Range r("fsb200:multi:upload_slice");
+            cu(c->in_xyz.ensure(3 * (size_t)n), "cudaMalloc");
+            cu(c->in_radii.ensure(n), "cudaMalloc");
+            if (d == 0) cu(c->out_sasa.ensure(n), "cudaMalloc");
+            cu(cudaEventCreateWithFlags(&uploaded[d], cudaEventDisableTiming), "cudaEventCreate");
+            if (rc[d] == FSB200_SUCCESS && ensure_stage(c, 32 * (size_t)(cnt > 0 ? cnt : 1) + (d == 0 ? 8 * (size_t)n : 0))) check(FSB200_FAIL);
+            if (rc[d] == FSB200_SUCCESS && cnt > 0) {
+                check(staged_h2d(c, c->in_xyz.p + 3 * (size_t)a0, xyz + 3 * (size_t)a0, 24 * (size_t)cnt, 0, st));
+                check(staged_h2d(c, c->in_radii.p + a0, radii + a0, 8 * (size_t)cnt, 24 * (size_t)cnt, st));
+            }
+            if (uploaded[d]) cu(cudaEventRecord(uploaded[d], st), "cudaEventRecord");
+        }
+        barrier.wait();   // every slice is on its way, every buffer exists
+        if (!failed.load()) {
+            // phase 2: all-gather of the inputs over NVLink — pull every peer's slice once its upload has completed
+            Range r("fsb200:multi:gather_inputs");
+            for (int k = 1; k < N; ++k) {
+                const int p = (d + k) % N;   // staggered, so that not everybody pulls from device 0 first
+                const int b0 = fsb200_shard_begin(n, p, N), b1 = fsb200_shard_end(n, p, N);
+                if (b1 <= b0) continue;
+                cu(cudaStreamWaitEvent(st, uploaded[p], 0), "cudaStreamWaitEvent");
+                cu(cudaMemcpyPeerAsync(c->in_xyz.p + 3 * (size_t)b0, c->device, ctx[p]->in_xyz.p + 3 * (size_t)b0, ctx[p]->device,
+                                       24 * (size_t)(b1 - b0), st), "cudaMemcpyPeerAsync");
+                cu(cudaMemcpyPeerAsync(c->in_radii.p + b0, c->device, ctx[p]->in_radii.p + b0, ctx[p]->device, 8 * (size_t)(b1 - b0), st),
+                   "cudaMemcpyPeerAsync");
+            }
+        }
+        if (d == 0) ms.upload_ms = (float)ms_since(t_begin);
+        if (!failed.load()) {
+            // phase 3: cell list (replicated) + my share of the atoms; areas go straight to device 0 (peer stores)
+            Range r("fsb200:multi:integrate_shard");
+            Request rq{alg, resolution, probe, n, 1, nullptr, c->in_xyz.p, c->in_radii.p, ctx[0]->out_sasa.p, nullptr, d, N, st};
+            rq.sorted_output = 0;
+            check(run_pipeline(c, rq, [](cudaStream_t) { return FSB200_SUCCESS; }));
+            if (rc[d] == FSB200_SUCCESS && d < FSB200_MAX_DEVICES) {
+                ms.integrate_ms[d] = c->stats.integrate_ms;
+                ms.device_ms[d] = c->stats.device_ms;
+                ms.n_certified += 0;
+            }
+        }
+        barrier.wait();   // all shards are in device 0's buffer
+        if (d == 0) ms.compute_ms = (float)ms_since(t_begin) - ms.upload_ms;
+        if (d == 0 && !failed.load()) {
+            Range r("fsb200:multi:download");
+            double *h_out = reinterpret_cast<double *>(c->h_stage + 32 * (size_t)(cnt > 0 ? cnt : 1));
+            cu(cudaMemcpyAsync(h_out, c->out_sasa.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+            cu(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+            if (rc[d] == FSB200_SUCCESS) parallel_copy({{sasa, h_out, 8 * (size_t)n}});
+        }
+    };
+    {
+        std::vector<std::thread> helpers;
+        helpers.reserve(N);
+        for (int d = 1; d < N; ++d) {
+            try {
+                helpers.emplace_back(work, d);
+            } catch (...) {   // cannot start a helper thread: the call fails, but the started ones must not wait for it
+                failed.store(true);
+                rc[d] = FSB200_FAIL;
+                err[d] = "cannot start a host thread";
+                for (int e = d; e < N; ++e) barrier.drop();
+                break;
+            }
+        }
+        work(0);
+        for (auto &h : helpers) h.join();
+    }
+    ms.total_ms = (float)ms_since(t_begin);
+    ms.download_ms = ms.total_ms - ms.upload_ms - ms.compute_ms;
+    for (int d = 0; d < N; ++d) {
+        if (uploaded[d]) {
+            DeviceGuard guard(ctx[d]->device);
+            cudaStreamSynchronize(ctx[d]->stream);   // nobody may still be pulling from a context that goes back to the pool
+            cudaEventDestroy(uploaded[d]);
+        }
+    }
+    for (int d = 0; d < N; ++d) pool_release(ctx[d]);
+    {
+        std::lock_guard<std::mutex> g(g_multi_stats_lock);
+        g_multi_stats = ms;
+    }
+    for (int d = 0; d < N; ++d)
+        if (rc[d] != FSB200_SUCCESS) return fail("device %d: %.480s", devs[d], err[d].c_str());
+    return FSB200_SUCCESS;
+}
+
+int multi_batch(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
+                double *const *sasa, double probe, int resolution, const std::vector<int> &devs)
+{
+    const int N = (int)devs.size();
+    // longest-processing-time first on the atom counts (deterministic)
+    std::vector<int> order(n_struct);
+    for (int k = 0; k < n_struct; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_atoms[a] > n_atoms[b]; });
+    std::vector<long long> load(N, 0);
+    std::vector<std::vector<int>> mine(N);
+    for (int k : order) {
+        int best = 0;
+        for (int d = 1; d < N; ++d)
+            if (load[d] < load[best]) best = d;
+        mine[best].push_back(k);
+        load[best] += n_atoms[k] > 0 ? n_atoms[k] : 0;
+    }
+    std::vector<int> rc(N, FSB200_SUCCESS);
+    std::vector<std::string> err(N);
+    fsb200_multi_stats ms{};
+    ms.n_devices = N;
+    ms.n_structures = n_struct;
+    for (int d = 0; d < N; ++d) ms.n_atoms += (int)load[d];
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto work = [&](int d) {
+        std::vector<int> &idx = mine[d];
+        if (idx.empty()) return;
+        std::sort(idx.begin(), idx.end());
+        Range r("fsb200:multi:batch_share");
+        cudaSetDevice(devs[d]);
+        const size_t m = idx.size();
+        std::vector<int> cnt(m);
+        std::vector<const double *> px(m), pr(m);
+        std::vector<double *> ps(m);
+        for (size_t k = 0; k < m; ++k) {
+            cnt[k] = n_atoms[idx[k]];
+            px[k] = xyz[idx[k]];
+            pr[k] = radii[idx[k]];
+            ps[k] = sasa[idx[k]];
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        rc[d] = fsb200_calc_batch(alg, (int)m, cnt.data(), px.data(), pr.data(), ps.data(), probe, resolution);
+        if (rc[d] != FSB200_SUCCESS) err[d] = g_error;
+        if (d < FSB200_MAX_DEVICES) ms.device_ms[d] = (float)ms_since(t0);   // wall time of this device's share
+    };
+    {
+        std::vector<std::thread> helpers;
+        for (int d = 1; d < N; ++d) helpers.emplace_back(work, d);
+        const int prev = default_device();
+        work(0);
+        if (prev >= 0) cudaSetDevice(prev);
+        for (auto &h : helpers) h.join();
+    }
+    ms.total_ms = (float)ms_since(t_begin);
+    ms.compute_ms = ms.total_ms;
+    {
+        std::lock_guard<std::mutex> g(g_multi_stats_lock);
+        g_multi_stats = ms;
+    }
+    for (int d = 0; d < N; ++d)
+        if (rc[d] != FSB200_SUCCESS) return fail("device %d: %.480s", devs[d], err[d].c_str());
+    return FSB200_SUCCESS;
+}
+
+}  // namespace
+
+int fsb200_calc_multi(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
+                      double *const *sasa, double probe, int resolution, int n_devices)
+{
+    return guarded([&]() -> int {
+        if (n_struct <= 0 || !n_atoms || !xyz || !radii || !sasa) return fail("invalid batch arguments");
+        std::vector<int> devs;
+        const int visible = fsb200_device_count();
+        for (int d = 0; d < visible; ++d) {
+            int major = 0;
+            if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) devs.push_back(d);
+        }
+        if (devs.empty()) return fail("no sm_100 device visible: the engine has no CPU path");
+        if (n_devices <= 0) n_devices = (int)devs.size();
+        if (n_devices > (int)devs.size()) return fail("%d devices requested, %d usable", n_devices, (int)devs.size());
+        if (n_devices > FSB200_MAX_DEVICES) return fail("at most %d devices", FSB200_MAX_DEVICES);
+        devs.resize(n_devices);
+        Range r("fsb200:calc_multi");
+        if (n_struct == 1) {
+            if (n_atoms[0] <= 0 || !xyz[0] || !radii[0] || !sasa[0]) return fail("structure 0 is empty or has a null array");
+            // too small to be worth a second GPU: one device, the ordinary path
+            if (n_devices == 1 || n_atoms[0] < 16384 * n_devices) {
+                DeviceGuard guard(devs[0]);
+                return fsb200_calc_batch(alg, 1, n_atoms, xyz, radii, sasa, probe, resolution);
+            }
+            return multi_replicated(alg, n_atoms[0], xyz[0], radii[0], sasa[0], probe, resolution, devs);
+        }
+        if (n_devices == 1) {
+            DeviceGuard guard(devs[0]);
+            return fsb200_calc_batch(alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
+        }
+        for (int k = 0; k < n_struct; ++k)
+            if (n_atoms[k] <= 0 || !xyz[k] || !radii[k] || !sasa[k]) return fail("structure %d is empty or has a null array", k);
+        return multi_batch(alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution, devs);
+    });
+}
+
+int fsb200_lr_multi(double *sasa, const double *xyz, const double *radii, int n, double probe, int n_slices, int n_devices)
+{
+    if (!sasa || !xyz || !radii) return fail("null array");
+    return fsb200_calc_multi(FSB200_LEE_RICHARDS, 1, &n, &xyz, &radii, &sasa, probe, n_slices, n_devices);
+}
+
+int fsb200_sr_multi(double *sasa, const double *xyz, const double *radii, int n, double probe, int n_points, int n_devices)
+{
+    if (!sasa || !xyz || !radii) return fail("null array");
+    return fsb200_calc_multi(FSB200_SHRAKE_RUPLEY, 1, &n, &xyz, &radii, &sasa, probe, n_points, n_devices);
+}
+
+int fsb200_last_stats(fsb200_stats *out)
+{
+    if (!out) return fail("null argument");
+    *out = g_last_stats;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_get_multi_stats(fsb200_multi_stats *out)
+{
+    if (!out) return fail("null argument");
+    std::lock_guard<std::mutex> g(g_multi_stats_lock);
+    *out = g_multi_stats;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_trim(void)
+{
+    std::vector<fsb200_ctx *> idle;
+    {
+        std::lock_guard<std::mutex> g(g_pool_lock);
+        idle.swap(g_pool);
+    }
+    for (fsb200_ctx *c : idle) fsb200_ctx_destroy(c);
+    return (int)idle.size();
 }
 
 int fsb200_lr(double *sasa, const double *xyz, const double *radii, int n, double probe, int n_slices)

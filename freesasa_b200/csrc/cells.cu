@@ -112,15 +112,28 @@ __global__ void k_grid(Workspace ws)
     double edge = 2.0 * rmax * (1.0 + 1e-9);
     if (!(edge > 0.0)) edge = 1.0;  // all radii zero: nobody can have a neighbour
     const double cap = (double)kCellsPerAtomCap * (a1 - a0) + kCellsSlack;
-    for (;;) {
-        double cells = 1.0;
-        for (int k = 0; k < 3; ++k) {
-            const double ext = floor((hi[k] - lo[k]) / edge) + 1.0;
-            cells *= ext;
-            g.dim[k] = ext < 2.0e9 ? (int)ext : 2000000000;
+    // Every coordinate is finite (k_bounds checked), but the EXTENT hi - lo can still overflow to +inf (x = +-9e307):
+    // then inf/edge = inf, inf/inf = NaN and `cells <= cap` would be false forever.  Such input is reported as bad input;
+    // the loop is bounded in any case (1.26^3100 overflows a double, so a finite extent is always settled long before).
+    bool settled = false;
+    if (isfinite(hi[0] - lo[0]) && isfinite(hi[1] - lo[1]) && isfinite(hi[2] - lo[2])) {
+        for (int iter = 0; iter < 4096 && !settled; ++iter) {
+            double cells = 1.0;
+            for (int k = 0; k < 3; ++k) {
+                const double ext = floor((hi[k] - lo[k]) / edge) + 1.0;
+                cells *= ext;
+                g.dim[k] = ext < 2.0e9 ? (int)ext : 2000000000;
+            }
+            settled = cells <= cap;
+            if (!settled) edge *= 1.26;
         }
-        if (cells <= cap) break;
-        edge *= 1.26;
+    }
+    if (!settled) {
+        atomicExch(ws.counters + kCtrBadInput, 1);
+        for (int k = 0; k < 3; ++k) { g.lo[k] = 0; g.dim[k] = 1; }
+        g.edge = 1.0;
+        ws.grid[sid] = g;
+        return;
     }
     for (int k = 0; k < 3; ++k) g.lo[k] = lo[k];
     g.edge = edge;
@@ -237,7 +250,8 @@ __global__ void __launch_bounds__(256) k_reorder(Workspace ws)
     const double R = ws.radii[i] + ws.probe;
     ws.atoms[pos] = make_double4(ws.xyz[3 * i], ws.xyz[3 * i + 1], ws.xyz[3 * i + 2], R);
     ws.perm[pos] = i;
-    if (rank % kItemAtoms == 0) {
+    const int chunk_end = min(pos - rank % kItemAtoms + kItemAtoms, end);   // end of this atom's kItemAtoms-chunk
+    if (rank % kItemAtoms == 0 && pos < ws.shard_end && chunk_end > ws.shard_begin) {   // other shards' items are never queued
         const int sid = ws.n_struct == 1 ? 0 : find_structure(ws.offsets, ws.n_struct, i);
         Item it;
         it.sid = sid;

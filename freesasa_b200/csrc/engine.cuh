@@ -22,7 +22,32 @@
 
 namespace fsb200 {
 
-constexpr int kWarpsPerCta = 14;            // warps claim atoms dynamically from the CTA's ring of staged tiles
+// Build-time experiment knobs.  The defaults ARE the product; tests/tools/ab_variants.py builds variants side by side
+// (libfsb200_<name>.so) to measure one change at a time on the GPU box.
+#ifndef FSB200_WARPS
+#define FSB200_WARPS 14
+#endif
+#ifndef FSB200_FUSED_VOTES
+#define FSB200_FUSED_VOTES 1      // slice loop: one REDUX.OR instead of 2 + K votes
+#endif
+#ifndef FSB200_EXACT_SLICES
+#define FSB200_EXACT_SLICES 1     // fp32 L&R: slices with a near-tangent circle pair are redone in fp64
+#endif
+
+#ifndef FSB200_NEAR_FLOOR
+#define FSB200_NEAR_FLOOR 3.0e-6f // marginal band of the fp32 L&R path: q = min(|N|,|D|)/max(|N|,|D|) below this ...
+#endif
+#ifndef FSB200_NEAR_SCALE
+#define FSB200_NEAR_SCALE 1.26e-6f // ... or below this x (slice thickness x Ri)^2 (thick slices need a wider band)
+#endif
+#ifndef FSB200_RING_ATOMICS
+#define FSB200_RING_ATOMICS 1     // ring protocol through acquire/release atomics (0: round 1's volatile polls, for A/B timing)
+#endif
+#ifndef FSB200_COMPACT_CERT
+#define FSB200_COMPACT_CERT 0     // certificate: do not unroll the retry / open-direction loops (smaller SASS)
+#endif
+
+constexpr int kWarpsPerCta = FSB200_WARPS;  // warps claim atoms dynamically from the CTA's ring of staged tiles
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr int kRingSlots = 2;               // tiles in flight per CTA
 constexpr int kItemAtoms = 16;              // one work item = up to 16 consecutive atoms of one cell
@@ -32,6 +57,7 @@ constexpr int kCertPoints = 128;           // probe directions of the buried-ato
 constexpr int kCertPairs = kCertPoints / 2;
 constexpr int kCellsPerAtomCap = 2;         // grid budget: cells <= 2*n_k + 64 per structure
 constexpr int kCellsSlack = 64;
+constexpr int kMaxPeers = 8;                // other buffers (usually on other GPUs) one call can mirror its areas into
 
 // Per-structure uniform grid, computed on the device.
 struct GridDesc {
@@ -90,6 +116,10 @@ struct Workspace {
     int *scan_tmp;     // block sums for the scan
     int *counters;     // kCtrCount ints
     int *overflow;     // n     sorted positions of overflow atoms
+    // output sharding of ONE replicated problem: only work items that touch sorted positions [shard_begin, shard_end)
+    // are emitted by k_reorder, so a shard's queue holds its own items only (0, n = everything)
+    int shard_begin;
+    int shard_end;
 };
 
 struct IntegrateArgs {
@@ -105,6 +135,11 @@ struct IntegrateArgs {
     const double *points_d;   // SR: unit test points, 3*resolution doubles (bit-identical to the reference's)
     int grid_ctas;
     const float4 *cert_points;  // non-null: use the buried-atom certificate; kCertPairs unit vectors (the set is these and their negatives)
+    // Fused collective: besides `out`, every area is also stored at the same index of these buffers, which may live on
+    // OTHER GPUs (peer memory over NVLink: cudaDeviceEnablePeerAccess in one process, CUDA IPC between processes) — the
+    // all-gather of the per-atom areas happens store by store from the integration epilogue, 8 B per atom and peer.
+    int n_peer_out;
+    double *peer_out[kMaxPeers];
 };
 
 // cells.cu

@@ -17,6 +17,7 @@
 
 #include <assert.h>
 #include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -119,6 +120,51 @@ static int validate(const char *alg, const char *func, int n_atoms, int n_thread
     return 0;
 }
 
+/* FREESASA_B200_DEVICES=<n|all>: the drop-in entry points spread ONE call over n GPUs (fsb200_calc_multi: a structure of a
+ * million atoms is replicated and its outputs partitioned; a batch is dealt structure by structure).  Default: one GPU. */
+static int multi_devices(void)
+{
+    static int cached = -2;
+    if (cached == -2) {
+        const char *e = getenv("FREESASA_B200_DEVICES");
+        if (!e || !*e) cached = 1;
+        else if (strcmp(e, "all") == 0 || strcmp(e, "ALL") == 0) cached = 0;
+        else cached = atoi(e) > 0 ? atoi(e) : 1;
+    }
+    return cached;
+}
+
+/* FREESASA_B200_VERBOSE=1: one line per engine call on the error stream (freesasa_set_err_out, src/util.c:131-141) with
+ * what the device did — the engine itself never prints. */
+static void verbose_line(const char *what)
+{
+    static int on = -1;
+    fsb200_stats s;
+    FILE *fp;
+    if (on < 0) {
+        const char *e = getenv("FREESASA_B200_VERBOSE");
+        on = e && *e && strcmp(e, "0") != 0;
+    }
+    if (!on || verbosity == FREESASA_V_SILENT) return;
+    fp = errlog ? errlog : stderr;
+    if (multi_devices() != 1) {
+        fsb200_multi_stats m;
+        if (fsb200_get_multi_stats(&m) == FSB200_SUCCESS && m.n_devices > 1) {
+            fprintf(fp, "%s: B200 engine: %s: %d atoms in %d structure(s) on %d GPUs: upload %.3f ms, compute %.3f ms, download %.3f ms, "
+                        "total %.3f ms\n", prog, what, m.n_atoms, m.n_structures, m.n_devices, m.upload_ms, m.compute_ms, m.download_ms,
+                    m.total_ms);
+            fflush(fp);
+            return;
+        }
+    }
+    if (fsb200_last_stats(&s) != FSB200_SUCCESS) return;
+    fprintf(fp, "%s: B200 engine: %s: %d atoms in %d structure(s): device %.3f ms (integration kernel %.3f ms, %d launches), "
+                "%d atoms proved buried, %d work items, %d large neighbourhoods; host: staging %.3f ms, whole call %.3f ms\n",
+            prog, what, s.n_atoms, s.n_structures, s.device_ms, s.integrate_ms, s.kernel_launches, s.n_certified, s.n_items,
+            s.n_overflow, s.host_stage_ms, s.host_total_ms);
+    fflush(fp);
+}
+
 int freesasa_lee_richards(double *sasa, const coord_t *c, const double *radii, const freesasa_parameters *param)
 {
     int rc;
@@ -127,8 +173,11 @@ int freesasa_lee_richards(double *sasa, const coord_t *c, const double *radii, c
     assert(radii);
     if (param == NULL) param = &freesasa_default_parameters;
     if (validate("L&R", __func__, c->n, param->n_threads, param->lee_richards_n_slices, &rc)) return rc;
-    if (fsb200_lr(sasa, c->xyz, radii, c->n, param->probe_radius, param->lee_richards_n_slices) != FSB200_SUCCESS)
+    if ((multi_devices() == 1 ? fsb200_lr(sasa, c->xyz, radii, c->n, param->probe_radius, param->lee_richards_n_slices)
+                              : fsb200_lr_multi(sasa, c->xyz, radii, c->n, param->probe_radius, param->lee_richards_n_slices,
+                                                multi_devices())) != FSB200_SUCCESS)
         return FAIL_MSG("B200 engine: %s", fsb200_last_error());
+    verbose_line("Lee & Richards");
     return FREESASA_SUCCESS;
 }
 
@@ -140,8 +189,11 @@ int freesasa_shrake_rupley(double *sasa, const coord_t *c, const double *radii, 
     assert(radii);
     if (param == NULL) param = &freesasa_default_parameters;
     if (validate("S&R", __func__, c->n, param->n_threads, param->shrake_rupley_n_points, &rc)) return rc;
-    if (fsb200_sr(sasa, c->xyz, radii, c->n, param->probe_radius, param->shrake_rupley_n_points) != FSB200_SUCCESS)
+    if ((multi_devices() == 1 ? fsb200_sr(sasa, c->xyz, radii, c->n, param->probe_radius, param->shrake_rupley_n_points)
+                              : fsb200_sr_multi(sasa, c->xyz, radii, c->n, param->probe_radius, param->shrake_rupley_n_points,
+                                                multi_devices())) != FSB200_SUCCESS)
         return FAIL_MSG("B200 engine: %s", fsb200_last_error());
+    verbose_line("Shrake & Rupley");
     return FREESASA_SUCCESS;
 }
 
@@ -248,13 +300,16 @@ int freesasa_calc_coord_batch(int n_struct, const double *const *xyz, const doub
         if (!results[k]) goto cleanup;
         sasa[k] = results[k]->sasa;
     }
-    if (fsb200_calc_batch((int)parameters->alg, n_struct, n_atoms, xyz, radii, sasa, parameters->probe_radius,
-                          resolution) != FSB200_SUCCESS) {
+    if ((multi_devices() == 1 ? fsb200_calc_batch((int)parameters->alg, n_struct, n_atoms, xyz, radii, sasa,
+                                                  parameters->probe_radius, resolution)
+                              : fsb200_calc_multi((int)parameters->alg, n_struct, n_atoms, xyz, radii, sasa,
+                                                  parameters->probe_radius, resolution, multi_devices())) != FSB200_SUCCESS) {
         FAIL_MSG("B200 engine: %s", fsb200_last_error());
         goto cleanup;
     }
     for (k = 0; k < n_struct; ++k) finish_result(results[k], parameters);
     free(sasa);
+    verbose_line("batch");
     return FREESASA_SUCCESS;
 cleanup:
     for (k = 0; k < n_struct; ++k) {

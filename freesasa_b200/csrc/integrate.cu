@@ -33,6 +33,7 @@ namespace fsb200 {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kStallPolls = 1 << 26;   // motionless polls of the ring before a warp reports a stall (>= 4 s)
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,20 +54,15 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
     const uint32_t addr = smem_addr(bar);
-    long long t0 = 0;
-    for (int spin = 0;; ++spin) {
+    for (int spin = 0; spin < (1 << 28); ++spin) {         // bounded by attempts, not by a clock (see the stall detector)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return true;
-        if ((spin & 1023) == 1023) {                       // ~2 s at 2 GHz: far beyond any legitimate wait
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) return false;
-        }
     }
+    return false;
 }
 // one non-blocking probe of the phase with the given parity
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
@@ -92,6 +88,17 @@ __device__ __forceinline__ unsigned lanemask_lt()
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+
+// ---- description of a staged fill (Slot::w below), one word per lane -------------------------------------
+// payload word indices: runs r = 0..8 of the 27-cell neighbourhood, then the scalars
+constexpr int kWBegin = 0;    // + r: first sorted position of run r
+constexpr int kWCount = 9;    // + r: atoms in run r
+constexpr int kWOff = 18;     // + r: tile index of run r's first atom
+constexpr int kWAtoms = 27;   // atoms in the item (0 for a dead slot)
+constexpr int kWFirst = 28;   // first sorted position of the item
+constexpr int kWTotal = 29;   // candidates in the neighbourhood
+constexpr int kWStaged = 30;  // 1: neighbourhood is in the slot's tile; 0: too large, read global memory
+constexpr int kWSelf = 31;    // tile index of sorted position p is w[kWSelf] + p
 
 // ---- per-warp record types ------------------------------------------------------------------------
 template <typename T> struct alignas(4 * sizeof(T)) Rec4 { T a, b, c, d; };   // raw {dx,dy,dz,R}; LR {dz,R,dxy,beta}; SR {dx,dy,dz,t}
@@ -165,8 +172,8 @@ __device__ __forceinline__ int gather_run(const double4 *base, int cnt, int skip
                     r.d = (T)Rj;
                 } else {
                     r.d = s.R > 0.0 ? (T)((s.R * s.R + d2 - Rj * Rj) / (2.0 * s.R)) : (T)0;
-                    cidx[slot] = index_base + c;
                 }
+                if (ALG == 1 || FSB200_EXACT_SLICES) cidx[slot] = index_base + c;   // S&R: exact re-check; L&R: fp64 redo
                 recs[slot] = r;
             }
         }
@@ -192,8 +199,11 @@ __device__ __forceinline__ void lr_prepare(Rec4<T> *recs, int nn, int lane)
     __syncwarp();
 }
 
+// `only`: when non-zero in any lane, just the slices whose bit is set are evaluated (lane w holds the bits of slices
+// 32 w .. 32 w + 31); used to redo marginal slices of the fp32 path in fp64
 template <typename T>
-__device__ __forceinline__ double lr_atom(const Rec4<T> *recs, Arc<T> *arcs, int nn, double Ri_d, int ns, int lane)
+__device__ __forceinline__ double lr_atom(const Rec4<T> *recs, Arc<T> *arcs, int nn, double Ri_d, int ns, int lane,
+                                          bool masked = false, unsigned only = 0u)
 {
     const T Ri = (T)Ri_d;
     const T two_pi = Consts<T>::two_pi();
@@ -202,6 +212,7 @@ __device__ __forceinline__ double lr_atom(const Rec4<T> *recs, Arc<T> *arcs, int
     double acc = 0.0;                                      // per-lane share of the exposed angle, all slices
 
     for (int s = 0; s < ns; ++s) {
+        if (masked && !((__shfl_sync(kFull, only, (s >> 5) & 31) >> (s & 31)) & 1u)) continue;
         const T zr = (T)(-Ri_d + (s + 0.5) * delta);       // slice centre relative to the atom centre (:305-307)
         const T az = fabs(zr);
         const T a2 = (Ri - az) * (Ri + az);                // Ri'^2 (:309), factored to avoid cancellation
@@ -313,14 +324,18 @@ __device__ __forceinline__ float atan_sqrt01(float q)
 }
 
 struct alignas(8) KeyArc {
-    int key;    // order-preserving bits of the arc start with the low 8 bits replaced by the arc index
-    float en;   // start + 2 alpha (may exceed 2 pi: the arc wraps)
+    int key;    // bits of the arc start: starts are >= 0, so the integers order exactly like the floats
+    float en;   // start + 2 alpha (may exceed one turn: the arc wraps)
 };
 
 // Exposed length contributed by this lane's arcs: sum_k max(0, start_k - max(W, P_k)) with
-// P_k = max{ en_m : key_m < key_k }.  arcs[0..narc) hold (unique key, end); sentinels are appended so the
-// loop can read four arcs at a time.  All lanes must call it (it synchronises the warp).
-__device__ __forceinline__ float merge_keyed(KeyArc *arcs, const float *starts, int narc, float W, int lane)
+// P_k = max{ en_m : (start_m, m) < (start_k, k) lexicographically } — the order of the reference's sorted sweep
+// (src/sasa_lr.c:367-408) without sorting, ties between equal starts broken by the arc index exactly as in lr_atom<T>.
+// (Round 1 replaced the low key bits by the arc index to save the tie test; that let two starts within 128 ulp swap order,
+// an error of up to that sliver per slice — 2e-4 A^2 at n_slices = 5.  The tie test costs one compare per FOUR arcs.)
+// arcs[0..narc) hold (start bits, end); sentinels are appended so the loop can read four arcs at a time.  All lanes must
+// call it (it synchronises the warp).
+__device__ __forceinline__ float merge_keyed(KeyArc *arcs, int narc, float W, int lane)
 {
     if (lane < 4) {
         KeyArc pad;
@@ -334,23 +349,29 @@ __device__ __forceinline__ float merge_keyed(KeyArc *arcs, const float *starts, 
     float sum = 0.f;
     for (int k = lane; k < narc; k += 32) {
         const int my_key = arcs[k].key;
+        const int kq = k >> 2;
         float P = W;
         for (int g = 0; g < n_quads; ++g) {
             const float4 lo = quad[2 * g], hi = quad[2 * g + 1];   // warp-uniform addresses: broadcast
-            if (__float_as_int(lo.x) < my_key) P = fmaxf(P, lo.y);
-            if (__float_as_int(lo.z) < my_key) P = fmaxf(P, lo.w);
-            if (__float_as_int(hi.x) < my_key) P = fmaxf(P, hi.y);
-            if (__float_as_int(hi.z) < my_key) P = fmaxf(P, hi.w);
+            const int thr = my_key + (g < kq ? 1 : 0);             // arcs of earlier quads precede me on equal starts too
+            if (__float_as_int(lo.x) < thr) P = fmaxf(P, lo.y);
+            if (__float_as_int(lo.z) < thr) P = fmaxf(P, lo.w);
+            if (__float_as_int(hi.x) < thr) P = fmaxf(P, hi.y);
+            if (__float_as_int(hi.z) < thr) P = fmaxf(P, hi.w);
         }
-        sum += fmaxf(starts[k] - P, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                              // my own quad: equal starts with a smaller index
+            const KeyArc o = arcs[4 * kq + j];
+            if (4 * kq + j < k && o.key == my_key) P = fmaxf(P, o.en);
+        }
+        sum += fmaxf(__int_as_float(my_key) - P, 0.f);
     }
     return sum;
 }
 
 // General fp32 path (any neighbour count): all arcs of a slice are compacted to shared memory and merged
 // pairwise with unique integer keys.
-__device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
-                                               double Ri_d, int ns, int lane)
+__device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *arcs, int nn, double Ri_d, int ns, int lane)
 {
     const float Ri = (float)Ri_d;
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
@@ -367,6 +388,7 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
         int narc = 0;
         bool buried = false;
         float my_max = 0.f;
+        __syncwarp();                                      // a buried slice may have left arcs of other lanes in the array
         for (int base = 0; base < nn; base += 32) {
             const int j = base + lane;
             const bool valid = j < nn;
@@ -395,10 +417,9 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
             if (has) {
                 const int slot = narc + __popc(m & lt);
                 KeyArc arc;
-                arc.key = (__float_as_int(st) & ~0xff) | (slot & 0xff);
+                arc.key = __float_as_int(st);
                 arc.en = en;
                 arcs[slot] = arc;
-                starts[slot] = st;
                 my_max = fmaxf(my_max, en);
             }
             narc += __popc(m);
@@ -409,7 +430,7 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
             continue;
         }
         my_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(my_max)));  // non-negative floats order like uints
-        acc += (double)merge_keyed(arcs, starts, narc, fmaxf(my_max - two_pi, 0.f), lane);
+        acc += (double)merge_keyed(arcs, narc, fmaxf(my_max - two_pi, 0.f), lane);
         if (lane == 0) acc += (double)fmaxf(two_pi - my_max, 0.f);
         __syncwarp();
     }
@@ -465,12 +486,19 @@ __device__ __forceinline__ void lr_prepare_sorted(Rec4<float> *recs, int nn, int
 struct HalfArc {
     float st, en;     // sectors; st in [0,32), en in [st, st+32]
     bool has, bur;
+    bool near;        // one of the circle-circle tests of this pair is within rounding distance of its boundary
 };
 
-__device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, float zr, float a)
+// q_min: a pair whose q = min(|N|,|D|) / max(|N|,|D|) is below it is MARGINAL: one of the three circle-circle tests of
+// src/sasa_lr.c:324-333 is within rounding distance of its boundary (N -> 0 with f1 or f2, D -> 0 with f3) and the
+// half-angle alpha = 2 atan sqrt(q) — a square root of the gap — amplifies the ~1e-7 relative rounding of a, b, d by
+// 1/sqrt(q).  fp32 can neither decide nor measure such a pair: its slice is marked and redone in fp64 after the loop
+// (lr_redo_exact).  (A slice plane that merely grazes sphere j gives a tiny circle b; if that circle reaches the rim of
+// the slice circle its q is tiny as well, so the same test covers it.)
+__device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, float zr, float a, float q_min)
 {
     HalfArc h;
-    h.st = 0.f; h.en = 0.f; h.has = false; h.bur = false;
+    h.st = 0.f; h.en = 0.f; h.has = false; h.bur = false; h.near = false;
     const float dj = fabsf(r.a - zr);
     const float b2 = (r.b - dj) * (r.b + dj);
     const bool act = valid && b2 > 0.f;
@@ -485,6 +513,9 @@ __device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, f
         // N, D kept in st/en until the burial vote is over
         h.st = f1 * f2;
         h.en = f3 * (ab + d);
+#if FSB200_EXACT_SLICES
+        h.near = act && fminf(fabsf(h.st), fabsf(h.en)) < q_min * fmaxf(fabsf(h.st), fabsf(h.en));
+#endif
     }
     return h;
 }
@@ -511,9 +542,11 @@ __device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
     return (h.has && cnt > 0) ? mask : 0u;
 }
 
+// `marginal` (in/out): when can_redo, slices containing a marginal pair are NOT evaluated; their bit is set instead
+// (lane w keeps slices 32 w .. 32 w + 31) and the caller redoes them in fp64
 template <int K>
-__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, float *starts, int nn,
-                                                double Ri_d, int ns, int lane)
+__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, int nn, double Ri_d, int ns, int lane,
+                                                bool can_redo, unsigned &marginal)
 {
     const float Ri = (float)Ri_d;
     const double delta = 2.0 * Ri_d / ns;
@@ -526,6 +559,11 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
         r[h] = recs[v[h] ? lane + 32 * h : 0];
     }
     double acc = 0.0;                                      // exposed angle in sectors
+    // An angular error e in one arc end costs delta * Ri * e of area, so thick slices (low resolution) need a wider
+    // marginal band: the error of a pair left to fp32 is ~ 2e-7 / sqrt(q).  Floor 3e-6 (the band round 1's branch
+    // measured: 1M atoms, PDB-rounded, n = 100: 4.5e-4 -> 7e-5 A^2), growing with (delta Ri)^2 to 2.4e-5 at n = 5.
+    const float dR = (float)(delta * Ri_d);
+    const float q_min = fmaxf(FSB200_NEAR_FLOOR, FSB200_NEAR_SCALE * dR * dR);
 
     for (int s = 0; s < ns; ++s) {
         const float zr = (float)(-Ri_d + (s + 0.5) * delta);
@@ -534,24 +572,48 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
         if (!(a2 > 0.f)) continue;
         const float a = fast_sqrt(a2);
         HalfArc h[K];
-        bool bur = false;
+        // ONE warp reduction settles everything the warp has to agree on before any angle is computed: bit 0 = some
+        // circle swallows the slice circle (src/sasa_lr.c:327), bit 1 = some pair is marginal, bit 3+i = group i has
+        // an arc.  (Round 1 used 2 + K votes here; the ballot was the hottest
+        // line of the kernel.)
+        bool bur = false, near = false;
+        unsigned flags = 0u;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            h[i].st = 0.f; h[i].en = 0.f; h[i].has = false; h[i].bur = false;
-            if (i == 0 || nn > 32 * i) h[i] = half_eval(r[i], v[i], zr, a);
+            h[i].st = 0.f; h[i].en = 0.f; h[i].has = false; h[i].bur = false; h[i].near = false;
+            if (i == 0 || nn > 32 * i) h[i] = half_eval(r[i], v[i], zr, a, q_min);
             bur = bur || h[i].bur;
+            near = near || h[i].near;
+            flags |= h[i].has ? (8u << i) : 0u;
         }
-        if (__any_sync(kFull, bur)) continue;                              // buried slice
-        unsigned any[K], any_all = 0u;
+        flags |= (bur ? 1u : 0u) | (near ? 2u : 0u);
+#if FSB200_FUSED_VOTES
+        const unsigned agreed = __reduce_or_sync(kFull, flags);
+#else
+        unsigned agreed = 0u;
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            any[i] = __ballot_sync(kFull, h[i].has);
-            any_all |= any[i];
+        for (int b = 0; b < 3 + K; ++b) if (b != 2) agreed |= __any_sync(kFull, (flags >> b) & 1u) ? (1u << b) : 0u;
+#endif
+        if (agreed & 3u) {
+            if (can_redo && (agreed & 2u)) {
+                // marginal slice (rare): unless some burial is decisive — not itself marginal — it is left to the fp64 redo
+                bool sure = false;
+#pragma unroll
+                for (int i = 0; i < K; ++i) sure = sure || (h[i].bur && !h[i].near);
+                if (!__any_sync(kFull, sure)) {
+                    if (lane == (s >> 5)) marginal |= 1u << (s & 31);
+                    continue;
+                }
+            }
+            if (agreed & 1u) continue;                                     // buried slice
         }
-        if (any_all == 0u) {                                               // free circle
+        if ((agreed >> 3) == 0u) {                                         // free circle
             if (lane == 0) acc += 32.0;
             continue;
         }
+        bool any[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) any[i] = (agreed >> (3 + i)) & 1u;
         unsigned mask = 0u;
 #pragma unroll
         for (int i = 0; i < K; ++i)
@@ -568,10 +630,9 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
             if (rel) {
                 const int slot = narc + __popc(b & lt);
                 KeyArc arc;
-                arc.key = (__float_as_int(h[i].st) & ~0x7f) | slot;   // <= 112 arcs here: 7 index bits, ties within 128 ulp
+                arc.key = __float_as_int(h[i].st);
                 arc.en = h[i].en;
                 arcs[slot] = arc;
-                starts[slot] = h[i].st;
                 my_max = fmaxf(my_max, h[i].en);
             }
             narc += __popc(b);
@@ -585,16 +646,15 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
                 const int slot = narc + __popc(b & lt);
                 const float st = (float)lane, en = (float)(lane + ones);
                 KeyArc arc;
-                arc.key = (__float_as_int(st) & ~0x7f) | slot;
+                arc.key = __float_as_int(st);
                 arc.en = en;
                 arcs[slot] = arc;
-                starts[slot] = st;
                 my_max = fmaxf(my_max, en);
             }
             narc += __popc(b);
         }
         my_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(my_max)));
-        acc += (double)merge_keyed(arcs, starts, narc, fmaxf(my_max - 32.f, 0.f), lane);
+        acc += (double)merge_keyed(arcs, narc, fmaxf(my_max - 32.f, 0.f), lane);
         if (lane == 0) acc += (double)fmaxf(32.f - my_max, 0.f);
         __syncwarp();
     }
@@ -742,10 +802,14 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     // are the ones that hide whole patches anyway.
     const float bars[4] = {kCertCos, 0.84339145f, 0.67559021f, 0.46174861f};   // cos(12.5, 32.5, 47.5, 62.5 deg)
     constexpr float kWide = 0.65f;   // cos(49.5 deg); measured optimum on the 100k globule (0.5: 0.508 ms, 0.65: 0.467, 0.85: 0.484)
+#if FSB200_COMPACT_CERT
+#pragma unroll 1
+#endif
     for (int attempt = 0; attempt < 4; ++attempt) {
         const float bar = bars[attempt];
         int n_back = 0;
         n_useful = 0;
+        if (attempt > 0) __syncwarp();                     // the list is rewritten by other lanes than in the last attempt
         for (int base = 0; base < nn; base += 32) {
             const int j = base + lane;
             float4 e = make_float4(0.f, 0.f, 0.f, 3.0e38f);
@@ -766,12 +830,12 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
                 }
             }
             const unsigned mf = __ballot_sync(kFull, useful && wide), mb = __ballot_sync(kFull, useful && !wide);
-            if (useful) {
-                const int slot = wide ? n_useful + __popc(mf & lt) : kCertList - 1 - (n_back + __popc(mb & lt));
-                if (slot >= 0 && slot < kCertList) list[slot] = e;
-            }
             n_useful += __popc(mf);
             n_back += __popc(mb);
+            if (useful) {   // (the bounds keep front and back apart even in an attempt that overflows and is discarded)
+                const int slot = wide ? n_useful - __popc(mf) + __popc(mf & lt) : kCertList - 1 - (n_back - __popc(mb) + __popc(mb & lt));
+                if (wide ? slot < kCertList - n_back : slot >= n_useful) list[slot] = e;
+            }
         }
         n_wide = n_useful;
         n_useful += n_back;
@@ -802,7 +866,11 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     const float4 c1 = lane + 32 < n_back ? list[kCertList - 1 - (lane + 32)] : none;
     __syncwarp();                                              // the list's memory is reused by the integrators
     bool ok = true;
+#if FSB200_COMPACT_CERT
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int q = 0; q < 4 && ok; ++q) {
         unsigned open = __ballot_sync(kFull, !(q == 0 ? p0 : q == 1 ? m0 : q == 2 ? p1 : m1));
         const float sign = (q & 1) ? -1.f : 1.f;
@@ -826,23 +894,67 @@ template <int ALG, typename T> struct WarpMem {
     Rec4<T> *recs;
     Arc<T> *arcs;      // L&R: arc_cap(cap) arcs of the current slice
     T *starts;         // L&R fp32 fast path: exact arc starts
-    int *cidx;         // S&R only
+    int *cidx;         // candidate positions: S&R after the records; L&R in the LAST cap ints of the warp's region (over the
+                       // tail of `starts`, dead until the slices begin; the certificate's list sits at the front of `arcs`)
     float4 *cert_list; // short list of the buried-atom certificate (kCertList entries)
     __device__ __forceinline__ WarpMem(unsigned char *mem, int cap)
     {
         recs = reinterpret_cast<Rec4<T> *>(mem);
         arcs = reinterpret_cast<Arc<T> *>(mem + (size_t)cap * sizeof(Rec4<T>));
         starts = reinterpret_cast<T *>(mem + (size_t)cap * sizeof(Rec4<T>) + (size_t)arc_cap(cap) * sizeof(Arc<T>));
-        cidx = reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
+        cidx = ALG == 0 ? reinterpret_cast<int *>(mem + WarpLayout<ALG, T>::bytes(cap) - (size_t)cap * sizeof(int))
+                        : reinterpret_cast<int *>(mem + (size_t)cap * sizeof(Rec4<T>));
         cert_list = ALG == 0 ? reinterpret_cast<float4 *>(arcs)
                              : reinterpret_cast<float4 *>(mem + (size_t)cap * (sizeof(Rec4<T>) + sizeof(int)));
     }
 };
 
+// Slices the fp32 path marked as marginal, redone with the generic integrator in fp64: the records are rebuilt from the
+// fp64 atoms in global memory (differences in the atom-local frame, as the gather forms them) INTO the warp's own
+// shared-memory region, whose fp32 contents are dead by now.  The gather left each neighbour's candidate index in `cidx`
+// (the tail of the warp's region, untouched by the slice loop): a tile index when the neighbourhood was staged — turned into
+// a sorted position with the fill's run table, which the warp still holds in registers (`pw`, one word per lane) although
+// the tile itself has long been recycled — or the sorted position itself.  Out of line and called after the slice loop, so
+// that its register needs do not touch the hot loop.  Needs 48 nn bytes (records + arcs): nn <= 94 of the <= 96 this path serves.
+constexpr int kRedoMaxNeighbours = 94;
+__device__ __noinline__ double lr_redo_exact(const double4 *atoms, unsigned char *warp_mem, const int *cidx, int pw, int nn,
+                                             double sx, double sy, double sz, double Ri, int ns, unsigned marginal, int lane)
+{
+    Rec4<double> *recs = reinterpret_cast<Rec4<double> *>(warp_mem);
+    Arc<double> *arcs = reinterpret_cast<Arc<double> *>(warp_mem + (size_t)kRedoMaxNeighbours * sizeof(Rec4<double>));
+    const bool staged = __shfl_sync(kFull, pw, kWStaged) != 0;
+    int pos[3];
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        const bool valid = lane + 32 * h < nn;
+        const int c = valid ? cidx[lane + 32 * h] : 0;
+        int r = 0;
+#pragma unroll
+        for (int q = 1; q < 9; ++q) r += c >= __shfl_sync(kFull, pw, kWOff + q) ? 1 : 0;   // runs are laid out in order
+        const int p = __shfl_sync(kFull, pw, kWBegin + r) + (c - __shfl_sync(kFull, pw, kWOff + r));
+        pos[h] = valid ? (staged ? p : c) : -1;
+    }
+    __syncwarp();                                          // the indices sit where the fp64 arcs go
+#pragma unroll
+    for (int h = 0; h < 3; ++h)
+        if (pos[h] >= 0) {
+            const double4 q = atoms[pos[h]];
+            const double dx = q.x - sx, dy = q.y - sy, dz = q.z - sz;
+            Rec4<double> o;
+            o.a = dz;
+            o.b = q.w;
+            o.c = sqrt(dx * dx + dy * dy);
+            o.d = atan2(dy, dx) + 3.141592653589793;
+            recs[lane + 32 * h] = o;
+        }
+    __syncwarp();
+    return lr_atom<double>(recs, arcs, nn, Ri, ns, lane, true, marginal);
+}
+
 template <int ALG, typename T, bool FAST>
 __device__ __forceinline__ bool finish_atom(const Workspace &ws, const IntegrateArgs &args, const WarpMem<ALG, T> &wm,
                                             const double4 *cand_base, const Self &s, int nn, int cap, int pos,
-                                            bool allow_overflow, int lane)
+                                            bool allow_overflow, int lane, int pw = 0)
 {
     __syncwarp();
     if (nn > cap) {
@@ -865,13 +977,17 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
             if constexpr (FAST && sizeof(T) == 4) {
                 Rec4<float> *recs = reinterpret_cast<Rec4<float> *>(wm.recs);
                 KeyArc *arcs = reinterpret_cast<KeyArc *>(wm.arcs);
-                float *starts = reinterpret_cast<float *>(wm.starts);
                 if (nn <= 96) {                            // ONE instantiation (K = 3) for all of them: the kernel is
-                    lr_prepare_sorted<3>(recs, nn, lane);  // instruction-cache sensitive (ncu: no_instruction stalls
-                    area = lr_atom_fastk<3>(recs, arcs, starts, nn, s.R, args.resolution, lane);  // with K = 1, 2, 3 side by side)
+                    const bool can_redo = FSB200_EXACT_SLICES && nn <= kRedoMaxNeighbours && args.resolution <= 1024;
+                    unsigned marginal = 0u;
+                    lr_prepare_sorted<3>(recs, nn, lane);           // instruction-cache sensitive (ncu: no_instruction stalls
+                    area = lr_atom_fastk<3>(recs, arcs, nn, s.R, args.resolution, lane, can_redo, marginal);  // with K = 1, 2, 3 side by side)
+                    if (__any_sync(kFull, marginal != 0u))
+                        area += lr_redo_exact(ws.atoms, reinterpret_cast<unsigned char *>(wm.recs), wm.cidx, pw, nn, s.x, s.y, s.z,
+                                              s.R, args.resolution, marginal, lane);
                 } else {
                     lr_prepare<float>(recs, nn, lane);
-                    area = lr_atom_fast(recs, arcs, starts, nn, s.R, args.resolution, lane);
+                    area = lr_atom_fast(recs, arcs, nn, s.R, args.resolution, lane);
                 }
             } else {
                 lr_prepare<T>(wm.recs, nn, lane);
@@ -883,7 +999,9 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
     }
     if (lane == 0) {
         const int i = ws.perm[pos];
-        args.out[args.sorted_output ? pos : i] = area;
+        const int idx = args.sorted_output ? pos : i;
+        args.out[idx] = area;
+        for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
         if (args.nn_out) args.nn_out[i] = nn | (certified ? (1 << 30) : 0);
     }
     return certified;
@@ -930,20 +1048,54 @@ struct Slot {
     int claim;        // (fill & 0xffff) << 16 | n_atoms << 8 | next unclaimed atom: ONE word, so that "is there an
                       // atom left in fill f" and the claim itself are decided on the same atomic snapshot
     int gathered;     // atoms of this fill whose neighbour gather is complete
-    int n_atoms;      // atoms in the item (0 for a dead slot)
     int dead;         // the global queue was empty when this slot was last refilled: no more fills here
-    int first;        // first sorted position of the item
-    int total;        // candidates in the neighbourhood
-    int staged;       // 1: neighbourhood is in the slot's tile; 0: too large, read global memory
-    int self_off;     // tile index of sorted position p is self_off + p
-    int begin[9], count[9], off[9];
+    int pad;
+    int w[32];        // the fill's description, ONE WORD PER LANE: a warp writes / reads it with a single warp-wide
+                      // atomic and looks fields up with shuffles (kW* below)
 };
-
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+// Memory-model hygiene of the ring.  EVERY word of a slot that another warp may read or write concurrently — cur, claim,
+// gathered, dead and the 32 payload words — is accessed only through block-scope atomic read-modify-write operations with
+// acquire / release semantics: a reader that observes a published claim word (acquire) is guaranteed to see the payload
+// written before it (release); the last gather's acq_rel increment of `gathered` orders every reader of a fill before the
+// refill that overwrites it; and compute-sanitizer's racecheck sees atomics on both sides of every pair.  Round 1 used plain
+// stores + __threadfence_block() against volatile polls: it worked on sm_100 but was a formal data race (62 racecheck
+// reports).  FSB200_RING_ATOMICS=0 rebuilds that protocol for A/B timing only.
+#if FSB200_RING_ATOMICS
+__device__ __forceinline__ int ld_acquire(int *p)
+{
+    int v;
+    asm volatile("atom.acquire.cta.shared::cta.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    int old;
+    asm volatile("atom.release.cta.shared::cta.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr(p)), "r"(v) : "memory");
+    (void)old;
+}
+__device__ __forceinline__ int cas_acq_rel(int *p, int expected, int desired)
+{
+    int old;
+    asm volatile("atom.acq_rel.cta.shared::cta.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(smem_addr(p)), "r"(expected), "r"(desired) : "memory");
+    return old;
+}
+__device__ __forceinline__ int add_acq_rel(int *p, int v)
+{
+    int old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr(p)), "r"(v) : "memory");
+    return old;
+}
+#else
+__device__ __forceinline__ int ld_acquire(int *p) { return *reinterpret_cast<volatile int *>(p); }
+__device__ __forceinline__ void st_release(int *p, int v) { __threadfence_block(); *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ int cas_acq_rel(int *p, int expected, int desired) { return atomicCAS(p, expected, desired); }
+__device__ __forceinline__ int add_acq_rel(int *p, int v) { __threadfence_block(); return atomicAdd(p, v); }
+#endif
+__device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }   // global counters only
 
 // executed by one full warp: stage fill number `fill` into slot sl
 __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateArgs &args, int n_items, Slot *sl,
@@ -955,12 +1107,12 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
         if (lane == 0) idx = atomicAdd(ws.counters + kCtrQueue, 1);
         idx = __shfl_sync(kFull, idx, 0);
         if (idx >= n_items) {
+            st_release(&sl->w[lane], 0);
+            __syncwarp();
             if (lane == 0) {
-                sl->n_atoms = 0;
-                sl->dead = 1;
-                sl->gathered = 0;
-                sl->claim = (fill & 0xffff) << 16;             // n_atoms = 0, next = 0
-                __threadfence_block();
+                st_release(&sl->gathered, 0);
+                st_release(&sl->dead, 1);
+                st_release(&sl->claim, (fill & 0xffff) << 16);  // n_atoms = 0, next = 0
                 mbar_arrive(bar);
             }
             return;
@@ -980,21 +1132,19 @@ __device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateAr
         const int total = __shfl_sync(kFull, incl, 8);
         const int off4 = __shfl_sync(kFull, off, 4), b4 = __shfl_sync(kFull, b, 4);
         const bool staged = total <= kTileCap;
-        if (lane < 9) {
-            sl->begin[lane] = b;
-            sl->count[lane] = n;
-            sl->off[lane] = off;
+        {   // the fill's description, one word per lane, written with ONE warp-wide atomic
+            const int r = lane % 9;
+            const int rb = __shfl_sync(kFull, b, r), rn = __shfl_sync(kFull, n, r), ro = __shfl_sync(kFull, off, r);
+            const int word = lane < kWCount ? rb : lane < kWOff ? rn : lane < kWAtoms ? ro
+                           : lane == kWAtoms ? it.count : lane == kWFirst ? it.first : lane == kWTotal ? total
+                           : lane == kWStaged ? (staged ? 1 : 0) : off4 - b4;
+            st_release(&sl->w[lane], word);
         }
+        __syncwarp();                                      // all 32 words are written
         if (lane == 0) {
-            sl->n_atoms = it.count;
-            sl->gathered = 0;
-            sl->first = it.first;
-            sl->total = total;
-            sl->staged = staged ? 1 : 0;
-            sl->self_off = off4 - b4;
-            sl->claim = ((fill & 0xffff) << 16) | (it.count << 8);
+            st_release(&sl->gathered, 0);
+            st_release(&sl->claim, ((fill & 0xffff) << 16) | (it.count << 8));   // publishes the payload above
         }
-        __threadfence_block();
         __syncwarp();
         if (staged) {
             if (lane == 0) {
@@ -1023,11 +1173,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     unsigned char *warp_mem = smem + (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
     const WarpMem<ALG, T> wm(warp_mem, kNbCap);
     const int n_items = ws.counters[kCtrItems] + ws.counters[kCtrItemsBack];
+    if (ws.counters[kCtrBadInput]) return;                 // the call fails anyway (uniform exit: nothing is armed yet)
     if (tid == 0) {
         cur = 0;
         for (int s = 0; s < kRingSlots; ++s) {
             slots[s].dead = 0;
-            slots[s].n_atoms = 0;
             slots[s].gathered = 0;
             slots[s].claim = ((s - kRingSlots) & 0xffff) << 16;   // "one fill older than the first": not ready yet
             mbar_init(&full[s], 1);
@@ -1037,7 +1187,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     if (warp == 0)
         for (int s = 0; s < kRingSlots; ++s) fill_slot(ws, args, n_items, &slots[s], tiles + (size_t)s * kTileCap, &full[s], s, lane);
 
-    long long wait_since = 0;
+    int idle_polls = 0, last_seen = -1;
     int n_certified = 0;
     for (;;) {
         // ---- claim one atom (lane 0 negotiates, the warp follows) ----------------------------------------
@@ -1047,15 +1197,15 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         // before anybody noticed it was exhausted), an EARLIER one means the refill is still to come.
         int code = 0, f = 0, a = 0;                        // code 0: look again, 1: atom claimed, 2: all work done, 3: stalled
         if (lane == 0) {
-            f = ld_volatile(&cur);
+            f = ld_acquire(&cur);
             Slot *sl = &slots[f % kRingSlots];
-            if (ld_volatile(&sl->dead)) {
+            if (ld_acquire(&sl->dead)) {
                 bool all = true;
-                for (int t = 0; t < kRingSlots; ++t) all = all && ld_volatile(&slots[t].dead) != 0;
+                for (int t = 0; t < kRingSlots; ++t) all = all && ld_acquire(&slots[t].dead) != 0;
                 if (all) code = 2;
-                else atomicCAS(&cur, f, f + 1);
+                else cas_acq_rel(&cur, f, f + 1);
             } else {
-                const int w = ld_volatile(&sl->claim);
+                const int w = ld_acquire(&sl->claim);
                 const unsigned gen = (unsigned)w >> 16;
                 if (gen == (unsigned)(f & 0xffff)) {
                     if (mbar_test(&full[f % kRingSlots], (uint32_t)(f / kRingSlots) & 1u)) {
@@ -1063,22 +1213,30 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
                         // (a fill's atom count travels in the claim word: reading it from the slot instead let a
                         //  warp claim a non-existent atom of an exhausted one-atom fill whose slot was just being
                         //  recycled — caught by the self-check below on 1024-structure batches)
-                        if (a >= ((w >> 8) & 0xff)) atomicCAS(&cur, f, f + 1);             // fill exhausted: open the next one
-                        else if (atomicCAS(&sl->claim, w, w + 1) == w) code = 1;
+                        if (a >= ((w >> 8) & 0xff)) cas_acq_rel(&cur, f, f + 1);           // fill exhausted: open the next one
+                        else if (cas_acq_rel(&sl->claim, w, w + 1) == w) code = 1;
                     }
                 } else if (((gen - (unsigned)f) & 0xffffu) < 0x8000u) {
-                    atomicCAS(&cur, f, f + 1);
+                    cas_acq_rel(&cur, f, f + 1);
                 }
             }
             if (code == 0) {                               // nothing to do right now: back off, but never hang
-                const long long now = clock64();
-                if (wait_since == 0) wait_since = now;
-                else if (now - wait_since > 4000000000ll) {
+                // Stall detector: counts POLLS during which the ring did not move (cur and the polled claim word
+                // unchanged), not elapsed time — a context that is time-sliced out, single-stepped or run under
+                // compute-sanitizer polls slowly but is not stalled.  2^26 polls of >= 64 ns each is >= 4 s of
+                // continuous, motionless polling.
+                const int seen = f * 31 + ld_acquire(&slots[f % kRingSlots].claim);
+                if (seen != last_seen) {
+                    last_seen = seen;
+                    idle_polls = 0;
+                } else if (++idle_polls > kStallPolls) {
                     if (atomicExch(ws.counters + kCtrStalled, 1) == 0) {   // first reporter leaves a post-mortem
                         int *dbg = ws.counters + 7;
                         dbg[0] = f;
-                        dbg[1] = slots[0].claim; dbg[2] = slots[0].gathered; dbg[3] = slots[0].n_atoms * 2 + slots[0].dead;
-                        dbg[4] = slots[1].claim; dbg[5] = slots[1].gathered; dbg[6] = slots[1].n_atoms * 2 + slots[1].dead;
+                        dbg[1] = ld_acquire(&slots[0].claim); dbg[2] = ld_acquire(&slots[0].gathered);
+                        dbg[3] = ld_acquire(&slots[0].w[kWAtoms]) * 2 + ld_acquire(&slots[0].dead);
+                        dbg[4] = ld_acquire(&slots[1].claim); dbg[5] = ld_acquire(&slots[1].gathered);
+                        dbg[6] = ld_acquire(&slots[1].w[kWAtoms]) * 2 + ld_acquire(&slots[1].dead);
                         dbg[7] = (int)mbar_test(&full[0], 0) + 2 * (int)mbar_test(&full[0], 1) + 4 * (int)mbar_test(&full[1], 0) + 8 * (int)mbar_test(&full[1], 1);
                         dbg[8] = ld_volatile(ws.counters + kCtrQueue);
                     }
@@ -1086,7 +1244,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
                 }
                 __nanosleep(64);
             } else {
-                wait_since = 0;
+                idle_polls = 0;
             }
         }
         code = __shfl_sync(kFull, code, 0);
@@ -1098,42 +1256,48 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         Slot *sl = &slots[s];
         double4 *tile = tiles + (size_t)s * kTileCap;
         mbar_wait(&full[s], (uint32_t)(f / kRingSlots) & 1u);     // every lane observes the completed phase (returns at once)
-        const int pos = sl->first + a, n_atoms = sl->n_atoms;
+        const int pw = ld_acquire(&sl->w[lane]);                  // the fill's description: one word per lane, fields by shuffle
+        const int n_atoms = __shfl_sync(kFull, pw, kWAtoms);
+        const int pos = __shfl_sync(kFull, pw, kWFirst) + a;
         const bool mine = pos >= args.shard_begin && pos < args.shard_end;
 
         // ---- gather: the only use of the tile ----------------------------------------------------------------
         Self me;
         int nn = 0;
         if (mine) {
-            if (sl->staged) {
-                const int self_idx = sl->self_off + pos;
+            const int begin4 = __shfl_sync(kFull, pw, kWBegin + 4);
+            if (__shfl_sync(kFull, pw, kWStaged)) {
+                const int self_idx = __shfl_sync(kFull, pw, kWSelf) + pos;
                 me = load_self(tile[self_idx]);
                 if (ALG == 0) {
-                    nn = gather_run<ALG, T>(tile, sl->total, self_idx, 0, me, wm.recs, wm.cidx, 0, kNbCap, lane);
+                    nn = gather_run<ALG, T>(tile, __shfl_sync(kFull, pw, kWTotal), self_idx, 0, me, wm.recs, wm.cidx, 0, kNbCap, lane);
                 } else {  // S&R keeps GLOBAL candidate positions (its exact re-check outlives the tile)
-                    for (int r = 0; r < 9; ++r)
-                        nn = gather_run<ALG, T>(tile + sl->off[r], sl->count[r], r == 4 ? pos - sl->begin[4] : -1, sl->begin[r], me,
-                                                wm.recs, wm.cidx, nn, kNbCap, lane);
+                    for (int r = 0; r < 9; ++r) {
+                        const int rb = __shfl_sync(kFull, pw, kWBegin + r);
+                        nn = gather_run<ALG, T>(tile + __shfl_sync(kFull, pw, kWOff + r), __shfl_sync(kFull, pw, kWCount + r),
+                                                r == 4 ? pos - begin4 : -1, rb, me, wm.recs, wm.cidx, nn, kNbCap, lane);
+                    }
                 }
             } else {  // oversized neighbourhood: read the candidates straight from global memory
                 me = load_self(ws.atoms[pos]);
-                for (int r = 0; r < 9; ++r)
-                    nn = gather_run<ALG, T>(ws.atoms + sl->begin[r], sl->count[r], r == 4 ? pos - sl->begin[4] : -1, sl->begin[r], me,
+                for (int r = 0; r < 9; ++r) {
+                    const int rb = __shfl_sync(kFull, pw, kWBegin + r);
+                    nn = gather_run<ALG, T>(ws.atoms + rb, __shfl_sync(kFull, pw, kWCount + r), r == 4 ? pos - begin4 : -1, rb, me,
                                             wm.recs, wm.cidx, nn, kNbCap, lane);
+                }
             }
         }
         __syncwarp();
         int g = 0;
         if (lane == 0) {
-            __threadfence_block();
-            const int w_now = ld_volatile(&sl->claim);
-            g = atomicAdd(&sl->gathered, 1) + 1;
+            const int w_now = ld_acquire(&sl->claim);
+            g = add_acq_rel(&sl->gathered, 1) + 1;         // release: my reads of the tile are done; acquire: the last one sees all
             // protocol self-check: the slot must still host my fill, and the count can never pass n_atoms
             if (((unsigned)w_now >> 16) != (unsigned)(f & 0xffff) || g > n_atoms) {
                 if (atomicExch(ws.counters + kCtrStalled, 2) == 0) {
                     int *dbg = ws.counters + 7;
-                    dbg[0] = f; dbg[1] = w_now; dbg[2] = g; dbg[3] = n_atoms * 2; dbg[4] = a; dbg[5] = sl->n_atoms; dbg[6] = pos;
-                    dbg[7] = -1; dbg[8] = ld_volatile(&cur);
+                    dbg[0] = f; dbg[1] = w_now; dbg[2] = g; dbg[3] = n_atoms * 2; dbg[4] = a; dbg[5] = ld_acquire(&sl->w[kWAtoms]); dbg[6] = pos;
+                    dbg[7] = -1; dbg[8] = ld_acquire(&cur);
                 }
             }
         }
@@ -1141,7 +1305,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
         if (g == n_atoms) fill_slot(ws, args, n_items, sl, tile, &full[s], f + kRingSlots, lane);  // last gather: recycle the slot
 
         // ---- integrate (no shared state besides the warp's own lists) -----------------------------------------
-        if (mine) n_certified += finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane) ? 1 : 0;
+        if (mine) n_certified += finish_atom<ALG, T, true>(ws, args, wm, ws.atoms, me, nn, kNbCap, pos, true, lane, pw) ? 1 : 0;
         __syncwarp();
     }
     if (lane == 0 && n_certified) atomicAdd(ws.counters + kCtrCertified, n_certified);

@@ -94,3 +94,86 @@ def calc_replicated_sharded(n: int, compute_shard: Callable[[int, int], "object"
 
     full = torch.cat([gathered[r, : hi - lo] for r, (lo, hi) in enumerate(bounds)])
     return unpermute(full)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Without a host round trip between the kernel and the collective
+# ---------------------------------------------------------------------------------------------------------
+def gather_after_enqueue(engine, enqueue: Callable[[], "object"], gather: Callable[["object"], "object"]):
+    """Two-half step: ``enqueue()`` puts the kernels on the stream (Engine.calc_device_async) and returns the device
+    tensor they write; ``gather(tensor)`` queues the collective BEHIND them on the same stream; only then comes the one
+    synchronisation (Engine.finish).  If the engine had to run its rare second pass (atoms with > 160 neighbours) after
+    the collective was queued, the collective is issued again so that no rank keeps stale values."""
+    local = enqueue()
+    out = gather(local)
+    if engine.finish() != 0:  # FSB200_SECOND_PASS
+        out = gather(local)
+        import torch
+
+        torch.cuda.current_stream().synchronize()
+    return out
+
+
+class PeerGather:
+    """The all-gather of per-atom areas WITHOUT a collective call: every rank owns one symmetric output buffer (CUDA IPC),
+    maps the buffers of all peers, and its integration kernel stores each area into ALL of them from its epilogue (8 B per
+    atom and peer over NVLink).  A step is
+        ready barrier -> calc_device_async (peer stores) -> done barrier -> finish
+    where the barriers are one-warp kernels flipping epoch flags in peer memory (fsb200_ctx_peer_barrier): no NCCL call and
+    no host synchronisation between the kernel and the exchange.  torch.distributed is used ONCE, at construction, to
+    exchange the 64-byte IPC handles."""
+
+    def __init__(self, engine, n_total: int, rank: int, world: int, slot=None):
+        """n_total doubles per symmetric buffer.  slot = (offset, count): this rank's kernel fills only that window of
+        every buffer (independent structures, one per rank, gathered side by side); None: the kernel indexes the whole
+        buffer (one replicated structure, outputs partitioned by shard)."""
+        import torch
+        import torch.distributed as dist
+
+        from . import IpcBuffer
+
+        self.engine, self.rank, self.world, self.n = engine, rank, world, int(n_total)
+        self.slot = slot
+        dev = engine.device
+        self.mine = IpcBuffer(dev, 8 * self.n)
+        self.flags = IpcBuffer(dev, 4 * 64)
+        handles = [None] * world
+        dist.all_gather_object(handles, (self.mine.handle, self.flags.handle))
+        self.peers, self.peer_flags = [], []
+        for r, (h_out, h_flag) in enumerate(handles):
+            if r == rank:
+                self.peers.append(self.mine)
+                self.peer_flags.append(self.flags)
+            else:
+                self.peers.append(IpcBuffer.open(dev, h_out, 8 * self.n))
+                self.peer_flags.append(IpcBuffer.open(dev, h_flag, 4 * 64))
+        self.out = self.mine.tensor(torch.float64, self.n)
+        off = 8 * int(slot[0]) if slot else 0
+        self.window = self.out[slot[0]:slot[0] + slot[1]] if slot else self.out
+        engine.set_peer_outputs([p.ptr + off for r, p in enumerate(self.peers) if r != rank])
+        dist.barrier()
+
+    def barrier(self):
+        self.engine.peer_barrier(self.rank, self.world, [f.ptr for f in self.peer_flags])
+
+    def step(self, enqueue: Callable[["object"], "object"]):
+        """enqueue(out) must call engine.calc_device_async(..., out=out).  Returns the complete result (this rank's
+        symmetric buffer) after the one synchronisation."""
+        self.barrier()          # every rank has consumed the previous result: its buffer may be overwritten
+        enqueue(self.window)
+        self.barrier()          # every rank's kernel — and with it every peer store into my buffer — is complete
+        rc = self.engine.finish()
+        if rc != 0:             # second pass ran after the barrier: agree on completion once more
+            import torch
+
+            self.barrier()
+            torch.cuda.current_stream().synchronize()
+        self.engine.peer_barrier_status()
+        return self.out
+
+    def close(self):
+        self.engine.set_peer_outputs([])
+        for r, (p, f) in enumerate(zip(self.peers, self.peer_flags)):
+            if r != self.rank:
+                p.close()
+                f.close()

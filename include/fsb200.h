@@ -22,8 +22,10 @@
  *     caller fetches the message with fsb200_last_error() and reports it through its own
  *     fail_msg() (src/freesasa_internal.h:29-32);
  *   - there is NO CPU fallback: without a usable sm_100 device every compute call fails loudly;
- *   - re-entrant: host-pointer calls use a per-thread context; no state survives a call other
- *     than cached device scratch.
+ *   - re-entrant: host-pointer calls borrow a context from a pool; no state survives a call other
+ *     than cached device scratch and pinned staging (bounded: see fsb200_trim());
+ *   - environment: FSB200_PRECISION=fp64 (all-fp64 kernels), FREESASA_B200_DEVICE=<k> (device of the context-free entry
+ *     points when the caller has not chosen one), FREESASA_B200_VERBOSE=1 (host layer prints one timing line per call).
  */
 #ifndef FSB200_H
 #define FSB200_H
@@ -80,6 +82,43 @@ int fsb200_sr(double *sasa, const double *xyz, const double *radii, int n, doubl
 int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *const *xyz,
                       const double *const *radii, double *const *sasa, double probe, int resolution);
 
+/* ---- several GPUs behind one call (single process, one host thread per device, no NCCL) ------------ */
+/* What SURVEY.md section 8(b) calls fsb200_batch(..., n_devices) / fsb200_lr_multi(..., n_devices): the multi-GPU form
+ * of the entry points above for a C caller of freesasa_calc_structure() (src/freesasa.c:144-153) or of the CLI's loop
+ * over structures (src/main.cc:334-362).  n_devices <= 0 means every visible sm_100 device.
+ *   n_struct == 1  one structure: inputs replicated (each device uploads 1/N over its own PCIe link, the rest is an
+ *                  all-gather of the inputs over NVLink peer copies), outputs partitioned (each device integrates its
+ *                  share of the cell-sorted atoms and stores the areas straight into device 0's result buffer over
+ *                  NVLink).  Whole-structure SASA: every atom sees all its neighbours (NOT the per-chain quantity of
+ *                  --separate-chains, src/structure.c:955-1081).  Results are bit-identical to the one-device call.
+ *   n_struct  > 1  independent structures dealt to the devices by longest-processing-time on their atom counts. */
+#define FSB200_MAX_DEVICES 16
+int fsb200_calc_multi(int alg, int n_struct, const int *n_atoms, const double *const *xyz,
+                      const double *const *radii, double *const *sasa, double probe, int resolution,
+                      int n_devices);
+int fsb200_lr_multi(double *sasa, const double *xyz, const double *radii, int n, double probe,
+                    int n_slices, int n_devices);
+int fsb200_sr_multi(double *sasa, const double *xyz, const double *radii, int n, double probe,
+                    int n_points, int n_devices);
+/* Host-side timing of the last fsb200_calc_multi() of the process (benchmark bookkeeping). */
+typedef struct fsb200_multi_stats {
+    int n_devices, n_atoms, n_structures, n_certified;
+    float upload_ms;   /* one structure: wall time until the input all-gather is enqueued on device 0 */
+    float compute_ms;  /* until every device has finished its share */
+    float download_ms; /* device 0 -> host */
+    float total_ms;    /* the whole call */
+    float integrate_ms[FSB200_MAX_DEVICES]; /* one structure: integration kernel per device (CUDA events) */
+    float device_ms[FSB200_MAX_DEVICES];    /* one structure: cell list + kernel per device; batch: wall time of the device's share */
+} fsb200_multi_stats;
+int fsb200_get_multi_stats(fsb200_multi_stats *out);
+/* Host memory policy of the context-free entry points: idle pooled contexts keep their device scratch, at most 4 per
+ * device, and give back pinned staging above 256 MiB when a call returns.  fsb200_trim() destroys every idle pooled
+ * context (device scratch, pinned staging, stream) and returns how many there were. */
+int fsb200_trim(void);
+
+/* Statistics of the last context-free call (fsb200_lr / _sr / _calc_batch) made by the calling thread. */
+int fsb200_last_stats(fsb200_stats *out);
+
 /* ---- explicit contexts (one per device / stream user) ----------------------------------------- */
 fsb200_ctx *fsb200_ctx_create(int device); /* NULL on failure */
 void fsb200_ctx_destroy(fsb200_ctx *ctx);
@@ -113,9 +152,46 @@ int fsb200_ctx_calc_device(fsb200_ctx *ctx, int alg, const double *d_xyz, const 
                            int n_total, int n_struct, const int *offsets, double probe,
                            int resolution, int shard_index, int shard_count, double *d_sasa,
                            void *stream);
+/* The same call in two halves, so that a collective (or anything else) can be queued on the stream BEHIND the
+ * integration kernel and BEFORE the one host synchronisation of the call:
+ *     fsb200_ctx_calc_device_async(...)   validates and enqueues everything, returns without waiting
+ *     ... ncclAllGather(d_sasa ...) on the same stream, result download, peer signalling ...
+ *     fsb200_ctx_finish(ctx)              waits, reads the status words; FSB200_SUCCESS, FSB200_FAIL, or
+ *                                         FSB200_SECOND_PASS: atoms with more than 160 neighbours (never seen in
+ *                                         proteins) were completed by a second kernel AFTER the work queued in between,
+ *                                         so that work (the collective) has to be issued again.
+ * No other call may use the context between the two halves. */
+#define FSB200_SECOND_PASS 1
+int fsb200_ctx_calc_device_async(fsb200_ctx *ctx, int alg, const double *d_xyz, const double *d_radii,
+                                 int n_total, int n_struct, const int *offsets, double probe,
+                                 int resolution, int shard_index, int shard_count, double *d_sasa,
+                                 void *stream);
+int fsb200_ctx_finish(fsb200_ctx *ctx);
+/* Fused all-gather: every area computed by later device-resident calls on ctx is ALSO stored, at the same index, into
+ * these n_peers buffers (n_total doubles each), which normally live on OTHER GPUs — peer memory of the same process
+ * (cudaDeviceEnablePeerAccess) or buffers opened from another process with fsb200_ipc_open().  With peers set, a sharded
+ * call writes the caller's atom order (not the sorted order), so after all shards have finished every buffer holds the
+ * complete result and no unpermute / NCCL all-gather is needed.  n_peers = 0 switches it off. */
+int fsb200_ctx_set_peer_outputs(fsb200_ctx *ctx, int n_peers, double *const *d_peer_sasa);
+/* CUDA IPC plumbing for the one-process-per-GPU case: allocate a device buffer that other processes can map, export its
+ * 64-byte handle, map a peer's buffer, unmap it. */
+int fsb200_ipc_alloc(int device, unsigned long long bytes, void **d_ptr, unsigned char handle[64]);
+int fsb200_ipc_open(int device, const unsigned char handle[64], void **d_ptr);
+int fsb200_ipc_close(int device, void *d_ptr);
+int fsb200_ipc_free(int device, void *d_ptr);
+/* Barrier between the GPUs of world ranks WITHOUT NCCL and without the host: enqueues a one-warp kernel on the stream that
+ * stores a new epoch into slot `rank` of every rank's flag array (d_flags[r]: `world` ints on rank r's GPU, zeroed, peer-
+ * mapped) and waits until all slots of its own array carry it.  Queued behind fsb200_ctx_calc_device_async() it completes
+ * when every rank's integration kernel — and with it every peer store into this rank's buffer — is done.  Bounded wait:
+ * fsb200_ctx_peer_barrier_status() (after a stream synchronisation) reports a peer that never arrived. world <= 9. */
+int fsb200_ctx_peer_barrier(fsb200_ctx *ctx, int rank, int world, int *const *d_flags, void *stream);
+int fsb200_ctx_peer_barrier_status(fsb200_ctx *ctx);
+/* Identifies the last pipeline run on ctx (stamps the permutation fsb200_ctx_unpermute() would use). */
+unsigned long long fsb200_ctx_generation(const fsb200_ctx *ctx);
 int fsb200_shard_begin(int n_total, int shard_index, int shard_count);
 int fsb200_shard_end(int n_total, int shard_index, int shard_count);
-/* d_out[perm[p]] = d_sorted[p] using the permutation of the last calc_device call on ctx. */
+/* d_out[perm[p]] = d_sorted[p] using the permutation of the last calc_device call on ctx.  Fails if any other call ran
+ * on the context since (it would have replaced the permutation). */
 int fsb200_ctx_unpermute(fsb200_ctx *ctx, const double *d_sorted, double *d_out, int n_total,
                          void *stream);
 

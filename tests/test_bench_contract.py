@@ -26,7 +26,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and d["config"]["atoms"] == 100000
+    assert "workload" in d["config"] and d["config"]["atoms_per_gpu"] == 100000
+    # both arms must describe the workload with the same keys and values (the driver compares `config` key by key)
+    import bench
+
+    assert d["config"] == bench.shared_config(bench.ALGS["lr"])
 
 
 def test_product_arm_fails_loudly_without_a_gpu():

@@ -407,3 +407,66 @@ def test_precision_from_the_environment():
         errs[mode] = float(out.strip().splitlines()[-1])
     assert errs["fp64"] < LR_TOL_FP64
     assert LR_TOL_FP64 < errs["fp32"] < LR_TOL_FP32
+
+
+# ---- the fp32 tail: near-tangent circle pairs and equal arc starts -------------------------------------------------
+LR_TOL_TAIL = 2e-4  # round-2 target at a million atoms, PDB-rounded coordinates, any resolution
+
+
+def test_marginal_slices_are_redone_in_fp64(eng32, eng64):
+    """Slices with a near-tangent pair of circles are skipped by the fp32 path and redone in fp64, and arcs with equal starts
+    are ordered exactly: on coordinates rounded to the three decimals of a PDB file (where exact tangencies and ties
+    happen) the fp32 engine must stay within 1.5e-4 A^2 of the reference at low resolution as well, and the certificate /
+    overflow paths must be unaffected."""
+    x, r = fs.workloads.globule(150000, seed=5)
+    x, r = np.round(x, 3), np.round(r, 2)
+    for slices in (5, 20, 100):
+        want = ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, slices)
+        got = eng32.calc(fs.LEE_RICHARDS, x, r, 1.4, slices)
+        assert maxerr(got, want) < 1.5e-4, slices
+        assert maxerr(eng64.calc(fs.LEE_RICHARDS, x, r, 1.4, slices), want) < LR_TOL_FP64
+
+
+def test_equal_arc_starts_are_ordered_like_the_reference(eng32):
+    """Atoms on an exact lattice (no jitter) give slices whose arcs share their start to the last bit; the union must not
+    depend on which of them comes first (src/sasa_lr.c:367-408 sorts, ties in input order)."""
+    g = np.arange(-7, 8) * 2.5
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    r = np.full(len(x), 1.8)
+    for slices in (4, 7, 20):
+        assert maxerr(eng32.calc(0, x, r, 1.4, slices), ob.oracle_calc(x, r, 0, 1.4, slices)) < LR_TOL_TAIL, slices
+
+
+# ---- full-size benchmark configurations C4, C5 and the million-atom PDB-rounded tail -------------------------------
+def test_full_size_c5_one_million_atom_shell(eng32):
+    """BASELINE.json configs[4]: one 1M-atom capsid-scale shell, L&R n_slices = 100, against the oracle for every atom."""
+    x, r = fs.workloads.capsid(1_000_000)
+    got = eng32.calc(fs.LEE_RICHARDS, x, r, 1.4, 100)
+    want = ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, 100)
+    assert maxerr(got, want) < LR_TOL_TAIL
+    assert abs(got.sum() - want.sum()) < 1e-6 * want.sum()
+
+
+def test_full_size_c4_batch_of_1024(eng32):
+    """BASELINE.json configs[3]: 1024 independent ~5k-atom structures, L&R n_slices = 50, through the context-free batch
+    entry point (overlapped sub-batches); 128 sampled structures against the oracle, every structure against a one-pass
+    call on an explicit context (bit-identical)."""
+    structs = fs.workloads.batch(1024, 4000, 6000, seed=0)
+    got = fs.calc_batch(fs.LEE_RICHARDS, structs, 1.4, 50)
+    assert [len(g) for g in got] == [len(b) for _, b in structs]
+    for k in range(0, 1024, 8):
+        want = ob.oracle_calc(structs[k][0], structs[k][1], ob.LEE_RICHARDS, 1.4, 50)
+        assert maxerr(got[k], want) < LR_TOL_TAIL, k
+    whole = eng32.calc_batch(fs.LEE_RICHARDS, structs[:200], 1.4, 50)
+    for a, b in zip(got[:200], whole):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_one_million_atoms_pdb_rounded_low_resolution(eng32):
+    """The hard case for fp32: a million atoms with coordinates rounded to 3 decimals, n_slices = 20 and 5."""
+    x, r = fs.workloads.globule(1_000_000, seed=5)
+    x, r = np.round(x, 3), np.round(r, 2)
+    for slices in (20, 5):
+        got = eng32.calc(fs.LEE_RICHARDS, x, r, 1.4, slices)
+        want = ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, slices)
+        assert maxerr(got, want) < LR_TOL_TAIL, slices
