@@ -349,8 +349,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    cpu_group = None
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
+        # host-side rendezvous for the long waits: an NCCL barrier is a KERNEL spinning on the waiting rank's GPU, which would
+        # steal SMs from rank 0's multi-GPU C call in the C4 / C5 section
+        cpu_group = dist.new_group(backend="gloo")
 
     # ---- inputs: one structure per rank ------------------------------------------------------------
     alg, res = spec["alg"], spec["resolution"]
@@ -539,7 +543,8 @@ def main():
                 line["extras_error"] = repr(e)
         emit_line = line
     if distributed:
-        dist.barrier()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=cpu_group)
     # ---- configs C4 / C5 through the multi-GPU C entry point: rank 0 drives ALL visible GPUs, the other ranks are idle ----
     if rank == 0:
         if not args.no_extras and not args.no_certificate and args.alg == "lr":
@@ -551,7 +556,7 @@ def main():
                 emit_line["configs_error"] = repr(e)
         emit(emit_line)
     if distributed:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         if pg is not None:
             pg.close()
         dist.destroy_process_group()

@@ -80,7 +80,7 @@ class Stats(ctypes.Structure):
         ("n_overflow", ctypes.c_int), ("max_neighbours", ctypes.c_int), ("n_certified", ctypes.c_int),
         ("kernel_launches", ctypes.c_int),
         ("device_ms", ctypes.c_float), ("integrate_ms", ctypes.c_float),
-        ("host_stage_ms", ctypes.c_float), ("host_total_ms", ctypes.c_float),
+        ("host_stage_ms", ctypes.c_float), ("host_total_ms", ctypes.c_float), ("n_marginal", ctypes.c_int),
     ]
 
     def as_dict(self):
@@ -357,6 +357,8 @@ class IpcBuffer:
         it.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(self.ptr), False), "version": 2}
         assert count * itemsize <= self.nbytes
         t = torch.as_tensor(it, device=torch.device("cuda", self.device))
+        if t.data_ptr() != int(self.ptr):
+            raise RuntimeError("IpcBuffer.tensor: torch copied the buffer instead of aliasing it")
         t._fsb200_keepalive = self
         return t
 

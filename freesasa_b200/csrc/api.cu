@@ -380,6 +380,7 @@ struct Request {
     bool device_call = false;
     int n_peer_out = 0;
     double *const *peer_out = nullptr;
+    int owner_slice = 0;     // > 0: results partitioned by caller index over peer_out[] (IntegrateArgs::owner_slice)
 };
 
 // A call is two halves.  enqueue_pipeline() validates and puts the whole device sequence on the stream — cell-list build
@@ -422,6 +423,7 @@ int enqueue_pipeline(fsb200_ctx *c, const Request &rq)
     ia.nn_out = rq.d_nn;
     ia.n_peer_out = rq.n_peer_out;
     for (int q = 0; q < rq.n_peer_out; ++q) ia.peer_out[q] = rq.peer_out[q];
+    ia.owner_slice = rq.owner_slice;
     if (rq.alg == FSB200_SHRAKE_RUPLEY) {
         if (ensure_points(c, rq.resolution, st)) return FSB200_FAIL;
         ia.points_f = c->points_f.p;
@@ -505,6 +507,7 @@ int finish_pipeline(fsb200_ctx *c, F after_second_pass)
     s.n_items = c->h_status[kCtrItems] + c->h_status[kCtrItemsBack];
     s.n_overflow = c->h_status[kCtrOverflow];
     s.n_certified = c->h_status[kCtrCertified];
+    s.n_marginal = c->h_status[kCtrMarginal];
     s.max_neighbours = 0;
     if (c->h_status[kCtrBadInput]) {
         g_launches += launches;
@@ -1175,8 +1178,9 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
 //     uploads only its 1/N slice of xyz / radii over its own PCIe link, then every device pulls the other slices from
 //     its peers (an all-gather of the inputs over NVLink, N-1 peer copies per device); every device builds the identical
 //     deterministic cell list, integrates only its contiguous share of the cell-sorted order, and stores each area
-//     straight into device 0's result buffer in the caller's order (peer store from the integration epilogue: the
-//     all-gather of the outputs costs no launch and no extra pass); device 0 downloads the result.
+//     straight into the result slice of the device that OWNS that part of the caller's array (peer store over NVLink
+//     from the integration epilogue: the exchange of the outputs costs no launch and no extra pass); every device then
+//     downloads its contiguous slice over its own PCIe link.
 //     Every atom sees ALL its neighbours — this is the whole-structure SASA, not the per-chain quantity of the
 //     reference's --separate-chains (src/structure.c:955-1081).
 //   * n_struct > 1 (independent structures, config C4): structures are dealt to the devices by longest-processing-time
@@ -1237,6 +1241,8 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
                      const std::vector<int> &devs)
 {
     const int N = (int)devs.size();
+    if (N > kMaxPeers) return fail("fsb200_calc_multi: one structure can be spread over at most %d devices", kMaxPeers);
+    const int slice = (n + N - 1) / N;   // caller indices [o * slice, (o + 1) * slice) of the result live on device o
     for (int a = 0; a < N; ++a)
         for (int b = 0; b < N; ++b)
             if (a != b && !enable_peer(devs[a], devs[b]))
@@ -1280,9 +1286,9 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
             Range r("fsb200:multi:upload_slice");
             cu(c->in_xyz.ensure(3 * (size_t)n), "cudaMalloc");
             cu(c->in_radii.ensure(n), "cudaMalloc");
-            if (d == 0) cu(c->out_sasa.ensure(n), "cudaMalloc");
+            cu(c->out_sasa.ensure(slice), "cudaMalloc");
             cu(cudaEventCreateWithFlags(&uploaded[d], cudaEventDisableTiming), "cudaEventCreate");
-            if (rc[d] == FSB200_SUCCESS && ensure_stage(c, 32 * (size_t)(cnt > 0 ? cnt : 1) + (d == 0 ? 8 * (size_t)n : 0))) check(FSB200_FAIL);
+            if (rc[d] == FSB200_SUCCESS && ensure_stage(c, 32 * (size_t)(cnt > 0 ? cnt : 1) + 8 * (size_t)slice)) check(FSB200_FAIL);
             if (rc[d] == FSB200_SUCCESS && cnt > 0) {
                 check(staged_h2d(c, c->in_xyz.p + 3 * (size_t)a0, xyz + 3 * (size_t)a0, 24 * (size_t)cnt, 0, st));
                 check(staged_h2d(c, c->in_radii.p + a0, radii + a0, 8 * (size_t)cnt, 24 * (size_t)cnt, st));
@@ -1308,8 +1314,15 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
         if (!failed.load()) {
             // phase 3: cell list (replicated) + my share of the atoms; areas go straight to device 0 (peer stores)
             Range r("fsb200:multi:integrate_shard");
-            Request rq{alg, resolution, probe, n, 1, nullptr, c->in_xyz.p, c->in_radii.p, ctx[0]->out_sasa.p, nullptr, d, N, st};
+            // the result is partitioned by caller index: owner o holds [o * slice, (o + 1) * slice); its buffer is addressed
+            // through a base shifted by -o * slice so that the kernel can index every owner's buffer with the caller index
+            double *owners[kMaxPeers];
+            for (int o = 0; o < N; ++o) owners[o] = ctx[o]->out_sasa.p - (size_t)o * slice;
+            Request rq{alg, resolution, probe, n, 1, nullptr, c->in_xyz.p, c->in_radii.p, c->out_sasa.p, nullptr, d, N, st};
             rq.sorted_output = 0;
+            rq.n_peer_out = N;
+            rq.peer_out = owners;
+            rq.owner_slice = slice;
             check(run_pipeline(c, rq, [](cudaStream_t) { return FSB200_SUCCESS; }));
             if (rc[d] == FSB200_SUCCESS && d < FSB200_MAX_DEVICES) {
                 ms.integrate_ms[d] = c->stats.integrate_ms;
@@ -1317,14 +1330,16 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
                 ms.n_certified += 0;
             }
         }
-        barrier.wait();   // all shards are in device 0's buffer
+        barrier.wait();   // every shard has delivered its areas to their owners
         if (d == 0) ms.compute_ms = (float)ms_since(t_begin) - ms.upload_ms;
-        if (d == 0 && !failed.load()) {
-            Range r("fsb200:multi:download");
+        const int o0 = d * slice, o1 = o0 + slice < n ? o0 + slice : n;
+        if (!failed.load() && o1 > o0) {
+            // phase 4: every device downloads ITS slice of the result over its own PCIe link, every thread copies its part out
+            Range r("fsb200:multi:download_slice");
             double *h_out = reinterpret_cast<double *>(c->h_stage + 32 * (size_t)(cnt > 0 ? cnt : 1));
-            cu(cudaMemcpyAsync(h_out, c->out_sasa.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+            cu(cudaMemcpyAsync(h_out, c->out_sasa.p, 8 * (size_t)(o1 - o0), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
             cu(cudaStreamSynchronize(st), "cudaStreamSynchronize");
-            if (rc[d] == FSB200_SUCCESS) parallel_copy({{sasa, h_out, 8 * (size_t)n}});
+            if (rc[d] == FSB200_SUCCESS) std::memcpy(sasa + o0, h_out, 8 * (size_t)(o1 - o0));
         }
     };
     {

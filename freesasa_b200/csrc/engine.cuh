@@ -43,6 +43,9 @@ namespace fsb200 {
 #ifndef FSB200_RING_ATOMICS
 #define FSB200_RING_ATOMICS 1     // ring protocol through acquire/release atomics (0: round 1's volatile polls, for A/B timing)
 #endif
+#ifndef FSB200_PIN_LANE
+#define FSB200_PIN_LANE 0
+#endif
 #ifndef FSB200_COMPACT_CERT
 #define FSB200_COMPACT_CERT 0     // certificate: do not unroll the retry / open-direction loops (smaller SASS)
 #endif
@@ -89,7 +92,8 @@ enum CounterSlot {
     kCtrStalled = 6,    // a warp gave up waiting for a tile (internal error, reported to the host)
     // 7..15: post-mortem of a stall; kCtrCertified shares slot 15 (only meaningful when nothing stalled)
     kCtrCertified = 15, // atoms proved completely buried by the coverage certificate (area 0 without integration)
-    kCtrCount = 16
+    kCtrMarginal = 16,  // atoms with at least one marginal Lee-Richards slice redone in fp64
+    kCtrCount = 20
 };
 
 // Plain data (no default member initialisers): api.cu zero-fills it and uses the bytes as the graph cache key.
@@ -140,6 +144,10 @@ struct IntegrateArgs {
     // all-gather of the per-atom areas happens store by store from the integration epilogue, 8 B per atom and peer.
     int n_peer_out;
     double *peer_out[kMaxPeers];
+    // owner_slice > 0: the result array is PARTITIONED by caller index over the buffers above — area of caller index i goes
+    // to peer_out[i / owner_slice][i] and nowhere else (multi-GPU C entry point: every GPU ends up holding one contiguous
+    // slice of the result, which it downloads over its own PCIe link)
+    int owner_slice;
 };
 
 // cells.cu

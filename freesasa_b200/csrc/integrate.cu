@@ -486,19 +486,12 @@ __device__ __forceinline__ void lr_prepare_sorted(Rec4<float> *recs, int nn, int
 struct HalfArc {
     float st, en;     // sectors; st in [0,32), en in [st, st+32]
     bool has, bur;
-    bool near;        // one of the circle-circle tests of this pair is within rounding distance of its boundary
 };
 
-// q_min: a pair whose q = min(|N|,|D|) / max(|N|,|D|) is below it is MARGINAL: one of the three circle-circle tests of
-// src/sasa_lr.c:324-333 is within rounding distance of its boundary (N -> 0 with f1 or f2, D -> 0 with f3) and the
-// half-angle alpha = 2 atan sqrt(q) — a square root of the gap — amplifies the ~1e-7 relative rounding of a, b, d by
-// 1/sqrt(q).  fp32 can neither decide nor measure such a pair: its slice is marked and redone in fp64 after the loop
-// (lr_redo_exact).  (A slice plane that merely grazes sphere j gives a tiny circle b; if that circle reaches the rim of
-// the slice circle its q is tiny as well, so the same test covers it.)
-__device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, float zr, float a, float q_min)
+__device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, float zr, float a)
 {
     HalfArc h;
-    h.st = 0.f; h.en = 0.f; h.has = false; h.bur = false; h.near = false;
+    h.st = 0.f; h.en = 0.f; h.has = false; h.bur = false;
     const float dj = fabsf(r.a - zr);
     const float b2 = (r.b - dj) * (r.b + dj);
     const bool act = valid && b2 > 0.f;
@@ -513,11 +506,68 @@ __device__ __forceinline__ HalfArc half_eval(const Rec4<float> &r, bool valid, f
         // N, D kept in st/en until the burial vote is over
         h.st = f1 * f2;
         h.en = f3 * (ab + d);
-#if FSB200_EXACT_SLICES
-        h.near = act && fminf(fabsf(h.st), fabsf(h.en)) < q_min * fmaxf(fabsf(h.st), fabsf(h.en));
-#endif
     }
     return h;
+}
+
+// ---- marginal slices, found BEFORE the slice loop ------------------------------------------------------------------
+// fp32 can neither decide nor measure a pair of slice circles that is within rounding distance of a tangency: with
+// N = (a+b-d)(d+b-a) and D = (d+a-b)(a+b+d) (the three comparisons of src/sasa_lr.c:324-333 are the signs of their factors)
+// the half-angle is alpha = 2 atan sqrt(N/D), a SQUARE ROOT of the gap, which amplifies the ~1e-7 relative rounding of a,
+// b, d by 1/sqrt(q), q = min(|N|,|D|)/max(|N|,|D|).  Such slices are left out of the fp32 loop and redone in fp64
+// (lr_redo_exact).  Round 2 first found them inside the loop (q < q_min for every pair of every slice: 4 instructions per
+// 32 pairs plus the vote — 7 % of the kernel, most of it instruction-cache pressure in the hottest loop); but WHERE a
+// pair is marginal is known in closed form: the circles of atoms i and j in the plane z are tangent exactly where that
+// plane touches the intersection circle of the two SPHERES, i.e. at its lowest and highest point
+//     z± = t dz/|D| ± rho dxy/|D|,   t = (|D|^2 + Ri^2 - Rj^2) / (2|D|),   rho^2 = Ri^2 - t^2
+// (centre line D = (dxy, dz), circle centre at distance t from atom i, radius rho).  Near z±, N (or D) crosses zero with
+// slope N' = 2 dz - 2 z dxy/a (D' = -2 dz - 2 z dxy/a), so q < q_min  <=>  |z - z±| < q_min |other| / |slope|.  One pass
+// over the neighbours (two heights each, ~150 instructions per 32 neighbours, once per atom instead of once per
+// slice) marks the slice planes inside those bands — with a factor 2 of safety, a floor for the fp32 records' own
+// rounding, and the whole interval between two heights that nearly coincide.  tests/tools/marginal_model.py checks the
+// construction against the brute-force q-test (it marks a superset, about twice as many slices).
+// Everything is fp32 (MUFU rsqrt / sqrt / rcp): the bands carry a slack for the rounding of z± itself, which grows like
+// 1/rho when the spheres barely intersect.
+// recs: prepared records {dz, R, dxy, beta}; side[0..31]: the bits, zeroed by the caller.
+__device__ __noinline__ void lr_mark_marginal(const Rec4<float> *recs, int *side, int nn, float Ri, int ns, float q_min, int lane)
+{
+    const float delta = 2.f * Ri / (float)ns, inv_delta = (float)ns / (2.f * Ri);
+    for (int j = lane; j < nn; j += 32) {
+        const Rec4<float> r = recs[j];
+        const float dz = r.a, Rj = r.b, d = r.c;
+        const float D3sq = fmaf(d, d, dz * dz);
+        if (!(D3sq > 0.f)) continue;
+        const float inv_D3 = rsqrtf(D3sq);
+        const float t = 0.5f * (D3sq + (Ri - Rj) * (Ri + Rj)) * inv_D3;
+        const float rho2 = (Ri - t) * (Ri + t);
+        if (!(rho2 > 0.f)) continue;                       // one sphere inside the other: their surfaces do not meet
+        const float rho = fast_sqrt(rho2);
+        const float zc = t * dz * inv_D3, ext = rho * d * inv_D3;
+        const float slack = 4.0e-6f * (1.f + fast_rcp(fmaxf(rho, 1.0e-3f)));
+        if (2.f * ext < 1.0e-3f) {                         // the two heights nearly coincide: everything in between is marginal
+            const float w = 1.0e-4f + slack;
+            const int s0 = max((int)floorf((zc - ext - w + Ri) * inv_delta - 0.5f), 0);
+            const int s1 = min((int)ceilf((zc + ext + w + Ri) * inv_delta - 0.5f), ns - 1);
+            for (int s = s0; s <= s1; ++s) atomicOr(&side[s >> 5], 1 << (s & 31));
+        }
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            const float z = k ? zc + ext : zc - ext;
+            const float a = fast_sqrt(fmaxf((Ri - z) * (Ri + z), 1.0e-12f));
+            const float zz = z - dz;
+            const float b = fast_sqrt(fmaxf((Rj - zz) * (Rj + zz), 0.f));
+            const float Nv = fabsf((a + b - d) * (d + b - a)), Dv = fabsf((d + a - b) * (a + b + d));
+            const float zda = 2.f * z * d * fast_rcp(a);
+            const float slope = Nv < Dv ? fabsf(2.f * dz - zda) : fabsf(-2.f * dz - zda);
+            const float eps = fminf(fmaxf(2.f * q_min * fmaxf(Nv, Dv) * fast_rcp(fmaxf(slope, 1.0e-9f)), 2.0e-6f) + 2.0e-6f + slack, delta);
+            const int sc = (int)rintf((z + Ri) * inv_delta - 0.5f);
+            for (int s = max(sc - 1, 0); s <= min(sc + 1, ns - 1); ++s) {
+                const float zs = fmaf((float)s + 0.5f, delta, -Ri);
+                if (fabsf(zs - z) < eps) atomicOr(&side[s >> 5], 1 << (s & 31));
+            }
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
@@ -542,11 +592,14 @@ __device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
     return (h.has && cnt > 0) ? mask : 0u;
 }
 
-// `marginal` (in/out): when can_redo, slices containing a marginal pair are NOT evaluated; their bit is set instead
-// (lane w keeps slices 32 w .. 32 w + 31) and the caller redoes them in fp64
+// `side`: 64 ints of the warp's shared memory that survive the slice loop (the tail of its region, behind the <= 96
+// candidate indices of the gather): side[0..31] are the bits of the MARGINAL slices (word s / 32), which this loop leaves
+// to the fp64 redo of the caller, and side[32..63] hold the fill's run table for that redo.  Keeping both out of registers
+// matters: the loop below runs at the kernel's register cap, and every extra live value turns into rematerialised address
+// arithmetic (ncu, round 2: 4 % of all issued instructions).
 template <int K>
-__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, int nn, double Ri_d, int ns, int lane,
-                                                bool can_redo, unsigned &marginal)
+__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, const int *side, int nn, double Ri_d,
+                                                int ns, int lane, bool masked)
 {
     const float Ri = (float)Ri_d;
     const double delta = 2.0 * Ri_d / ns;
@@ -559,13 +612,13 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
         r[h] = recs[v[h] ? lane + 32 * h : 0];
     }
     double acc = 0.0;                                      // exposed angle in sectors
-    // An angular error e in one arc end costs delta * Ri * e of area, so thick slices (low resolution) need a wider
-    // marginal band: the error of a pair left to fp32 is ~ 2e-7 / sqrt(q).  Floor 3e-6 (the band round 1's branch
-    // measured: 1M atoms, PDB-rounded, n = 100: 4.5e-4 -> 7e-5 A^2), growing with (delta Ri)^2 to 2.4e-5 at n = 5.
-    const float dR = (float)(delta * Ri_d);
-    const float q_min = fmaxf(FSB200_NEAR_FLOOR, FSB200_NEAR_SCALE * dR * dR);
 
     for (int s = 0; s < ns; ++s) {
+#if FSB200_EXACT_SLICES && !defined(FSB200_DBG_NO_BITTEST)
+        if (masked && ((side[s >> 5] >> (s & 31)) & 1)) continue;   // marginal: redone in fp64 (one broadcast shared-memory load)
+#endif
+        // slice centre relative to the atom centre (src/sasa_lr.c:305-307), formed in fp64 and rounded ONCE: a two-float
+        // fp32 version (one ulp instead of half an ulp of z) was measured at 3.4e-4 A^2 on the 1M-atom shell (2e-4 bar)
         const float zr = (float)(-Ri_d + (s + 0.5) * delta);
         const float az = fabsf(zr);
         const float a2 = (Ri - az) * (Ri + az);
@@ -573,47 +626,34 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
         const float a = fast_sqrt(a2);
         HalfArc h[K];
         // ONE warp reduction settles everything the warp has to agree on before any angle is computed: bit 0 = some
-        // circle swallows the slice circle (src/sasa_lr.c:327), bit 1 = some pair is marginal, bit 3+i = group i has
-        // an arc.  (Round 1 used 2 + K votes here; the ballot was the hottest
-        // line of the kernel.)
-        bool bur = false, near = false;
-        unsigned flags = 0u;
+        // circle swallows the slice circle (src/sasa_lr.c:327), bit 1+i = group i has an arc.
+        bool bur = false;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            h[i].st = 0.f; h[i].en = 0.f; h[i].has = false; h[i].bur = false; h[i].near = false;
-            if (i == 0 || nn > 32 * i) h[i] = half_eval(r[i], v[i], zr, a, q_min);
+            h[i].st = 0.f; h[i].en = 0.f; h[i].has = false; h[i].bur = false;
+            if (i == 0 || nn > 32 * i) h[i] = half_eval(r[i], v[i], zr, a);
             bur = bur || h[i].bur;
-            near = near || h[i].near;
-            flags |= h[i].has ? (8u << i) : 0u;
         }
-        flags |= (bur ? 1u : 0u) | (near ? 2u : 0u);
 #if FSB200_FUSED_VOTES
+        unsigned flags = bur ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < K; ++i) flags |= h[i].has ? (2u << i) : 0u;
         const unsigned agreed = __reduce_or_sync(kFull, flags);
 #else
-        unsigned agreed = 0u;
+        unsigned agreed = __any_sync(kFull, bur) ? 1u : 0u;
+        if (!agreed) {
 #pragma unroll
-        for (int b = 0; b < 3 + K; ++b) if (b != 2) agreed |= __any_sync(kFull, (flags >> b) & 1u) ? (1u << b) : 0u;
-#endif
-        if (agreed & 3u) {
-            if (can_redo && (agreed & 2u)) {
-                // marginal slice (rare): unless some burial is decisive — not itself marginal — it is left to the fp64 redo
-                bool sure = false;
-#pragma unroll
-                for (int i = 0; i < K; ++i) sure = sure || (h[i].bur && !h[i].near);
-                if (!__any_sync(kFull, sure)) {
-                    if (lane == (s >> 5)) marginal |= 1u << (s & 31);
-                    continue;
-                }
-            }
-            if (agreed & 1u) continue;                                     // buried slice
+            for (int i = 0; i < K; ++i) agreed |= __any_sync(kFull, h[i].has) ? (2u << i) : 0u;
         }
-        if ((agreed >> 3) == 0u) {                                         // free circle
+#endif
+        if (agreed & 1u) continue;                                         // buried slice
+        if ((agreed >> 1) == 0u) {                                         // free circle
             if (lane == 0) acc += 32.0;
             continue;
         }
         bool any[K];
 #pragma unroll
-        for (int i = 0; i < K; ++i) any[i] = (agreed >> (3 + i)) & 1u;
+        for (int i = 0; i < K; ++i) any[i] = (agreed >> (1 + i)) & 1u;
         unsigned mask = 0u;
 #pragma unroll
         for (int i = 0; i < K; ++i)
@@ -917,11 +957,14 @@ template <int ALG, typename T> struct WarpMem {
 // the tile itself has long been recycled — or the sorted position itself.  Out of line and called after the slice loop, so
 // that its register needs do not touch the hot loop.  Needs 48 nn bytes (records + arcs): nn <= 94 of the <= 96 this path serves.
 constexpr int kRedoMaxNeighbours = 94;
-__device__ __noinline__ double lr_redo_exact(const double4 *atoms, unsigned char *warp_mem, const int *cidx, int pw, int nn,
-                                             double sx, double sy, double sz, double Ri, int ns, unsigned marginal, int lane)
+constexpr int kSideWords = 96;   // cidx[96..127]: marginal-slice bits, cidx[128..159]: the fill's run table (kNbCap = 160 ints in all)
+__device__ __noinline__ double lr_redo_exact(const double4 *atoms, unsigned char *warp_mem, const int *cidx, int nn,
+                                             double sx, double sy, double sz, double Ri, int ns, int lane)
 {
     Rec4<double> *recs = reinterpret_cast<Rec4<double> *>(warp_mem);
     Arc<double> *arcs = reinterpret_cast<Arc<double> *>(warp_mem + (size_t)kRedoMaxNeighbours * sizeof(Rec4<double>));
+    const unsigned marginal = (unsigned)cidx[kSideWords + lane];
+    const int pw = cidx[kSideWords + 32 + lane];
     const bool staged = __shfl_sync(kFull, pw, kWStaged) != 0;
     int pos[3];
 #pragma unroll
@@ -979,12 +1022,26 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
                 KeyArc *arcs = reinterpret_cast<KeyArc *>(wm.arcs);
                 if (nn <= 96) {                            // ONE instantiation (K = 3) for all of them: the kernel is
                     const bool can_redo = FSB200_EXACT_SLICES && nn <= kRedoMaxNeighbours && args.resolution <= 1024;
-                    unsigned marginal = 0u;
+                    int *side = wm.cidx + kSideWords;
+                    side[lane] = 0;
+                    side[32 + lane] = pw;
                     lr_prepare_sorted<3>(recs, nn, lane);           // instruction-cache sensitive (ncu: no_instruction stalls
-                    area = lr_atom_fastk<3>(recs, arcs, nn, s.R, args.resolution, lane, can_redo, marginal);  // with K = 1, 2, 3 side by side)
-                    if (__any_sync(kFull, marginal != 0u))
-                        area += lr_redo_exact(ws.atoms, reinterpret_cast<unsigned char *>(wm.recs), wm.cidx, pw, nn, s.x, s.y, s.z,
-                                              s.R, args.resolution, marginal, lane);
+#ifdef FSB200_DBG_NO_PREPASS
+                    if (false) {
+#else
+                    if (can_redo) {                                 // with K = 1, 2, 3 side by side)
+#endif
+                        // thick slices (low resolution) need a wider band: an angular error e costs delta Ri e of area.  Floor
+                        // 3e-6 (1M atoms, PDB-rounded, n = 100: 4.5e-4 -> 7e-5 A^2), growing with (delta Ri)^2 to 2.4e-5 at n = 5
+                        const float dR = (float)(2.0 * s.R * s.R / args.resolution);
+                        lr_mark_marginal(recs, side, nn, (float)s.R, args.resolution, fmaxf(FSB200_NEAR_FLOOR, FSB200_NEAR_SCALE * dR * dR), lane);
+                    }
+                    area = lr_atom_fastk<3>(recs, arcs, side, nn, s.R, args.resolution, lane, can_redo);
+                    if (can_redo && __any_sync(kFull, side[lane] != 0)) {
+                        if (lane == 0) atomicAdd(ws.counters + kCtrMarginal, 1);
+                        area += lr_redo_exact(ws.atoms, reinterpret_cast<unsigned char *>(wm.recs), wm.cidx, nn, s.x, s.y, s.z,
+                                              s.R, args.resolution, lane);
+                    }
                 } else {
                     lr_prepare<float>(recs, nn, lane);
                     area = lr_atom_fast(recs, arcs, nn, s.R, args.resolution, lane);
@@ -1000,8 +1057,12 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
     if (lane == 0) {
         const int i = ws.perm[pos];
         const int idx = args.sorted_output ? pos : i;
-        args.out[idx] = area;
-        for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
+        if (args.owner_slice > 0) {
+            args.peer_out[idx / args.owner_slice][idx] = area;                     // to the GPU that owns this part of the result
+        } else {
+            args.out[idx] = area;
+            for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
+        }
         if (args.nn_out) args.nn_out[i] = nn | (certified ? (1 << 30) : 0);
     }
     return certified;
@@ -1168,7 +1229,13 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     __shared__ Slot slots[kRingSlots];
     __shared__ int cur;
 
+#if FSB200_PIN_LANE
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane;   // opaque to the optimiser: kept in a register instead of being re-derived (S2R + LOP) all over the loops
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+#else
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#endif
     double4 *tiles = reinterpret_cast<double4 *>(smem);
     unsigned char *warp_mem = smem + (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
     const WarpMem<ALG, T> wm(warp_mem, kNbCap);

@@ -62,6 +62,7 @@ typedef struct fsb200_stats {
     float integrate_ms;      /* device time of the integration kernel alone */
     float host_stage_ms;     /* host-pointer calls: wall time spent staging + enqueueing the upload */
     float host_total_ms;     /* host-pointer calls: wall time of the whole call */
+    int n_marginal;          /* L&R fp32: atoms with at least one near-tangent slice redone in fp64 */
 } fsb200_stats;
 
 /* ---- library / device -------------------------------------------------------------------- */
@@ -88,8 +89,9 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
  * over structures (src/main.cc:334-362).  n_devices <= 0 means every visible sm_100 device.
  *   n_struct == 1  one structure: inputs replicated (each device uploads 1/N over its own PCIe link, the rest is an
  *                  all-gather of the inputs over NVLink peer copies), outputs partitioned (each device integrates its
- *                  share of the cell-sorted atoms and stores the areas straight into device 0's result buffer over
- *                  NVLink).  Whole-structure SASA: every atom sees all its neighbours (NOT the per-chain quantity of
+ *                  share of the cell-sorted atoms and stores every area, over NVLink, straight into the result slice of the
+ *                  device that owns that part of the caller's array; each device downloads its slice over its own PCIe
+ *                  link).  At most 8 devices.  Whole-structure SASA: every atom sees all its neighbours (NOT the per-chain quantity of
  *                  --separate-chains, src/structure.c:955-1081).  Results are bit-identical to the one-device call.
  *   n_struct  > 1  independent structures dealt to the devices by longest-processing-time on their atom counts. */
 #define FSB200_MAX_DEVICES 16

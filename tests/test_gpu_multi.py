@@ -40,7 +40,12 @@ def _worker(rank, world, port, tmp):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     eng = fs.Engine(rank)
-    ok = True
+    failed = []
+
+    def check(name, cond):
+        if not bool(cond):
+            failed.append(name)
+
     # ---- C4 shape: batch of independent structures, LPT-sharded, one all-gather
     structs = workloads.batch(9, 300, 900, seed=2)
     sizes = [len(r) for _, r in structs]
@@ -54,7 +59,7 @@ def _worker(rank, world, port, tmp):
     outs = parallel.calc_batch_sharded(sizes, compute_mine)
     for k, (x, r) in enumerate(structs):
         err = np.abs(outs[k].cpu().numpy() - ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, 50)).max()
-        ok &= bool(err < 5e-4)
+        check(f"batch structure {k} vs oracle", err < 5e-4)
     # ---- C5 shape: one replicated structure, sorted-order output ranges, one all-gather, local un-permute
     x, r = workloads.capsid(40000, r_out=70.0, seed=3)
     dx, dr = torch.tensor(x, device=dev), torch.tensor(r, device=dev)
@@ -64,8 +69,8 @@ def _worker(rank, world, port, tmp):
 
     got = parallel.calc_replicated_sharded(len(r), compute_shard, eng.unpermute).cpu().numpy()
     whole = eng.calc_device(fs.LEE_RICHARDS, dx, dr, 1.4, 40).cpu().numpy()
-    ok &= bool(np.array_equal(got, whole))
-    ok &= bool(np.abs(got - ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, 40)).max() < 5e-4)
+    check("replicated+sharded (sync) equals one pass", np.array_equal(got, whole))
+    check("replicated+sharded vs oracle", np.abs(got - ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, 40)).max() < 5e-4)
     # ---- the same exchange without a host round trip: kernels enqueued, all-gather queued behind them, ONE synchronisation
     n = len(r)
     bounds = parallel.shard_bounds(n, world)
@@ -85,15 +90,16 @@ def _worker(rank, world, port, tmp):
 
     g = parallel.gather_after_enqueue(eng, enqueue, gather).view(world, width)
     full = torch.cat([g[q, : e - b] for q, (b, e) in enumerate(bounds)])
-    ok &= bool(np.array_equal(eng.unpermute(full).cpu().numpy(), whole))
+    check("two-half call + queued all-gather equals one pass", np.array_equal(eng.unpermute(full).cpu().numpy(), whole))
     # ---- and without any collective call: peer stores from the kernel epilogue + flag barriers over NVLink (CUDA IPC)
     pg = parallel.PeerGather(eng, n, rank, world)
-    for _ in range(3):
+    for it in range(3):
         got_peer = pg.step(lambda out: eng.calc_device_async(fs.LEE_RICHARDS, dx, dr, 1.4, 40, shard=(rank, world), out=out))
-        ok &= bool(np.array_equal(got_peer.cpu().numpy(), whole))
+        check(f"peer-store all-gather, step {it}: max diff {np.abs(got_peer.cpu().numpy() - whole).max():.3g}",
+              np.array_equal(got_peer.cpu().numpy(), whole))
     pg.close()
     with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
-        f.write("1" if ok else "0")
+        f.write("1" if not failed else "FAILED: " + "; ".join(failed))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -19,13 +19,12 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = {
     "product": [],
-    "r1_kernel": ["@integrate.cu=f4eaa4c"],          # integrate.cu of the round-1 commit, against today's api.cu / cells.cu
     "no_exact_slices": ["FSB200_EXACT_SLICES=0"],
-    "band_never": ["FSB200_NEAR_FLOOR=0.f", "FSB200_NEAR_SCALE=0.f"],     # detection compiled in, never fires
-    "band_x2": ["FSB200_NEAR_FLOOR=6.0e-6f", "FSB200_NEAR_SCALE=2.5e-6f"],
-    "votes_unfused": ["FSB200_FUSED_VOTES=0"],
+    "dbg_no_bittest": ["FSB200_DBG_NO_BITTEST=1"],     # timing only (marginal slices are counted twice)
+    "dbg_no_prepass": ["FSB200_DBG_NO_PREPASS=1"],     # timing only (nothing is marked)
+    "dbg_neither": ["FSB200_DBG_NO_PREPASS=1", "FSB200_DBG_NO_BITTEST=1"],
 }
-TAIL_VARIANTS = ("product", "band_x2")   # these also measure the 1M-atom PDB-rounded error tail
+TAIL_VARIANTS = ()   # these also measure the 1M-atom PDB-rounded error tail
 
 
 def lib_path(name):
