@@ -125,6 +125,11 @@ struct fsb200_ctx {
     DevBuf<double4> atoms;
     DevBuf<Item> items;
     DevBuf<unsigned char> scratch;
+    // split pipeline of the fp32 L&R path: task-record pool, record lists, control block
+    DevBuf<unsigned char> todo_pool;
+    DevBuf<unsigned long long> todo_list;
+    DevBuf<TodoCtl> todo_ctl;
+    bool split_pipeline = true;
     // Shrake-Rupley test points of the last resolution used
     // probe directions of the buried-atom certificate (uploaded once per context)
     DevBuf<float4> cert_points;
@@ -430,6 +435,22 @@ int enqueue_pipeline(fsb200_ctx *c, const Request &rq)
         ia.points_d = c->points_d.p;
     }
     ia.cert_points = c->use_certificate ? c->cert_points.p : nullptr;
+    if (FSB200_SPLIT && c->split_pipeline && rq.alg == FSB200_LEE_RICHARDS && c->precision == FSB200_FP32) {
+        // Task records of the atoms that have to be integrated: 1 KB per owned atom covers ~50 % of the atoms at the
+        // largest record (96 neighbours); if a call needs more, the remaining atoms are integrated inside k_integrate with
+        // the same arithmetic in the same order (bit-identical), only slower.
+        const size_t owned = (size_t)(ws.shard_end - ws.shard_begin);
+        size_t bytes = owned * 1024 + (4u << 20);
+        if (bytes > (16ull << 30)) bytes = 16ull << 30;
+        CU(c->todo_pool.ensure(bytes));
+        CU(c->todo_list.ensure(2 * (size_t)rq.n + 2));
+        CU(c->todo_ctl.ensure(1));
+        ia.todo_pool = c->todo_pool.p;
+        ia.todo_cap = bytes;
+        ia.todo_list = c->todo_list.p;
+        ia.todo_redo_base = rq.n + 1;
+        ia.todo_ctl = c->todo_ctl.p;
+    }
     int &ctas = c->grid_ctas[rq.alg][c->precision];
     if (ctas == 0) ctas = integrate_grid_ctas(rq.alg, c->precision, c->device);
     ia.grid_ctas = ctas;
@@ -726,6 +747,10 @@ fsb200_ctx *fsb200_ctx_create(int device)
     DeviceGuard guard(device);
     fsb200_ctx *c = new fsb200_ctx();
     c->device = device;
+    {   // FSB200_PIPELINE=fused: everything inside the one persistent kernel (round 1's layout; for A/B measurements)
+        const char *env = getenv("FSB200_PIPELINE");
+        if (env && strcmp(env, "fused") == 0) c->split_pipeline = false;
+    }
     {   // FSB200_PRECISION=fp64: the drop-in entry points (which have no precision argument) use the all-fp64 kernels
         const char *env = getenv("FSB200_PRECISION");
         if (env && (strcmp(env, "fp64") == 0 || strcmp(env, "FP64") == 0 || strcmp(env, "double") == 0)) c->precision = FSB200_FP64;
@@ -756,7 +781,8 @@ void fsb200_ctx_destroy(fsb200_ctx *c)
     c->offsets.release(); c->cell_of.release(); c->cell_start.release(); c->cell_fill.release();
     c->slot_atom.release(); c->perm.release(); c->scan_tmp.release(); c->counters.release();
     c->overflow.release(); c->bounds.release(); c->grid.release(); c->atoms.release();
-    c->items.release(); c->scratch.release(); c->barrier_status.release(); c->points_f.release(); c->points_d.release(); c->cert_points.release();
+    c->items.release(); c->scratch.release(); c->barrier_status.release();
+    c->todo_pool.release(); c->todo_list.release(); c->todo_ctl.release(); c->points_f.release(); c->points_d.release(); c->cert_points.release();
     for (int k = 0; k < 4; ++k)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);

@@ -43,6 +43,21 @@ namespace fsb200 {
 #ifndef FSB200_RING_ATOMICS
 #define FSB200_RING_ATOMICS 1     // ring protocol through acquire/release atomics (0: round 1's volatile polls, for A/B timing)
 #endif
+#ifndef FSB200_SPLIT
+#define FSB200_SPLIT 1            // fp32 L&R: k_integrate prepares, k_slices integrates chunks of slices, k_redo the marginal ones
+#endif
+#ifndef FSB200_CHUNK
+#define FSB200_CHUNK 16           // slices per task of k_slices (8: 0.523 ms, 16: 0.517 ms on C2; 4: slower)
+#endif
+#ifndef FSB200_SLICE_CTAS
+#define FSB200_SLICE_CTAS 4       // CTAs of k_slices per SM the compiler has to make room for (register cap)
+#endif
+#ifndef FSB200_RING_SLOTS
+#define FSB200_RING_SLOTS 2
+#endif
+#ifndef FSB200_TILE_CAP
+#define FSB200_TILE_CAP 640
+#endif
 #ifndef FSB200_PIN_LANE
 #define FSB200_PIN_LANE 0
 #endif
@@ -52,9 +67,9 @@ namespace fsb200 {
 
 constexpr int kWarpsPerCta = FSB200_WARPS;  // warps claim atoms dynamically from the CTA's ring of staged tiles
 constexpr int kCtaThreads = kWarpsPerCta * 32;
-constexpr int kRingSlots = 2;               // tiles in flight per CTA
+constexpr int kRingSlots = FSB200_RING_SLOTS; // tiles in flight per CTA
 constexpr int kItemAtoms = 16;              // one work item = up to 16 consecutive atoms of one cell
-constexpr int kTileCap = 640;               // atoms of the 27-cell neighbourhood staged in smem (20 KB)
+constexpr int kTileCap = FSB200_TILE_CAP;    // atoms of the 27-cell neighbourhood staged in smem (32 B each)
 constexpr int kNbCap = 160;                 // per-warp neighbour list capacity in smem
 constexpr int kCertPoints = 128;           // probe directions of the buried-atom certificate: kCertPairs antipodal pairs
 constexpr int kCertPairs = kCertPoints / 2;
@@ -126,6 +141,17 @@ struct Workspace {
     int shard_end;
 };
 
+// Control block of the split pipeline (zeroed per call, device memory)
+struct TodoCtl {
+    unsigned long long pool_head;   // bump allocator of the task-record pool (bytes)
+    int n_todo;                     // task records written by k_integrate
+    int task_head;                  // queue head of k_slices: task = (record, chunk of slices)
+    int n_redo;                     // records with marginal slices (fp64 redo tasks, the first tasks of k_slices)
+    int redo_head;                  // unused
+    int n_inline;                   // atoms integrated inside k_integrate because the pool was full
+    int pad;
+};
+
 struct IntegrateArgs {
     int alg;              // 0 LR, 1 SR
     int resolution;       // slices or points
@@ -148,12 +174,21 @@ struct IntegrateArgs {
     // to peer_out[i / owner_slice][i] and nowhere else (multi-GPU C entry point: every GPU ends up holding one contiguous
     // slice of the result, which it downloads over its own PCIe link)
     int owner_slice;
+    // Split pipeline of the fp32 Lee-Richards path (null pool = fused: everything inside k_integrate): k_integrate only
+    // gathers, certifies and PREPARES; atoms with exposed surface are written to the pool as task records and integrated by
+    // k_slices (chunks of slices from a queue), marginal slices by k_redo.
+    unsigned char *todo_pool;
+    unsigned long long todo_cap;         // bytes
+    unsigned long long *todo_list;       // [0, n): offsets of the task records; [todo_redo_base, +n): records with marginal slices
+    int todo_redo_base;
+    TodoCtl *todo_ctl;
 };
 
 // cells.cu
 int launch_cell_build(const Workspace &ws, cudaStream_t stream);   // returns number of launches
 // integrate.cu
 int launch_integrate(const Workspace &ws, const IntegrateArgs &args, cudaStream_t stream);
+size_t todo_pool_bytes_per_atom(int resolution);   // worst case of one task record
 int launch_overflow(const Workspace &ws, const IntegrateArgs &args, int n_overflow, int list_cap,
                     void *scratch, cudaStream_t stream);
 size_t overflow_scratch_bytes(int n_warps, int list_cap, int precision);

@@ -592,30 +592,30 @@ __device__ __forceinline__ unsigned half_finish(HalfArc &h, float beta_s)
     return (h.has && cnt > 0) ? mask : 0u;
 }
 
-// `side`: 64 ints of the warp's shared memory that survive the slice loop (the tail of its region, behind the <= 96
-// candidate indices of the gather): side[0..31] are the bits of the MARGINAL slices (word s / 32), which this loop leaves
-// to the fp64 redo of the caller, and side[32..63] hold the fill's run table for that redo.  Keeping both out of registers
-// matters: the loop below runs at the kernel's register cap, and every extra live value turns into rematerialised address
-// arithmetic (ncu, round 2: 4 % of all issued instructions).
+// The slice loop of the fp32 production path over ONE CHUNK of slices [s_begin, s_end).  An atom's slices are always
+// summed chunk by chunk (kernel k_slices works on chunks from a task queue, the fused path walks them in order), so that
+// the per-atom total has the same bits whichever way it was computed.
+//   r[K], v[K]   this lane's K prepared records {dz, R, dxy, beta in sectors} (z-sorted) and their validity
+//   marginal     bits of the slices that are left to the fp64 redo (word s / 32), or nullptr
+// Returns the exposed angle of the chunk in sectors (the same value in every lane).
+constexpr int kLrK = 3;   // at most 32 K = 96 neighbours in registers
+
+__host__ __device__ inline int lr_chunk_slices(int ns) { return ns <= 64 * FSB200_CHUNK ? FSB200_CHUNK : (ns + 63) / 64; }   // at most 64 chunks per atom
+__host__ __device__ inline int lr_n_chunks(int ns) { return (ns + lr_chunk_slices(ns) - 1) / lr_chunk_slices(ns); }
+
 template <int K>
-__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, const int *side, int nn, double Ri_d,
-                                                int ns, int lane, bool masked)
+__device__ __forceinline__ double lr_slices_chunk(const Rec4<float> (&r)[K], const bool (&v)[K], KeyArc *arcs,
+                                                  const unsigned *marginal, int nn, double Ri_d, int ns, int s_begin, int s_end,
+                                                  int lane)
 {
     const float Ri = (float)Ri_d;
     const double delta = 2.0 * Ri_d / ns;
     const unsigned lt = lanemask_lt();
-    Rec4<float> r[K];                                      // this lane's K records, for all slices of the atom
-    bool v[K];
-#pragma unroll
-    for (int h = 0; h < K; ++h) {
-        v[h] = lane + 32 * h < nn;
-        r[h] = recs[v[h] ? lane + 32 * h : 0];
-    }
     double acc = 0.0;                                      // exposed angle in sectors
 
-    for (int s = 0; s < ns; ++s) {
+    for (int s = s_begin; s < s_end; ++s) {
 #if FSB200_EXACT_SLICES && !defined(FSB200_DBG_NO_BITTEST)
-        if (masked && ((side[s >> 5] >> (s & 31)) & 1)) continue;   // marginal: redone in fp64 (one broadcast shared-memory load)
+        if (marginal && ((marginal[s >> 5] >> (s & 31)) & 1u)) continue;   // redone in fp64 (one uniform load)
 #endif
         // slice centre relative to the atom centre (src/sasa_lr.c:305-307), formed in fp64 and rounded ONCE: a two-float
         // fp32 version (one ulp instead of half an ulp of z) was measured at 3.4e-4 A^2 on the 1M-atom shell (2e-4 bar)
@@ -699,7 +699,25 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
         __syncwarp();
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-    return delta * Ri_d * acc * 0.19634954084936207;       // sectors -> radians (2 pi / 32)
+    return acc;
+}
+
+// all chunks of one atom in order (the fused path); recs: the warp's prepared records in shared memory
+template <int K>
+__device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc *arcs, const unsigned *marginal, int nn, double Ri_d,
+                                                int ns, int lane)
+{
+    Rec4<float> r[K];                                      // this lane's K records, for all slices of the atom
+    bool v[K];
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+        v[h] = lane + 32 * h < nn;
+        r[h] = recs[v[h] ? lane + 32 * h : 0];
+    }
+    const int S = lr_chunk_slices(ns);
+    double sum = 0.0;
+    for (int s0 = 0; s0 < ns; s0 += S) sum += lr_slices_chunk<K>(r, v, arcs, marginal, nn, Ri_d, ns, s0, min(s0 + S, ns), lane);
+    return (2.0 * Ri_d / ns) * Ri_d * sum * 0.19634954084936207;   // sectors -> radians (2 pi / 32)
 }
 
 // ---- step 3: Shrake & Rupley ---------------------------------------------------------------------
@@ -994,6 +1012,92 @@ __device__ __noinline__ double lr_redo_exact(const double4 *atoms, unsigned char
     return lr_atom<double>(recs, arcs, nn, Ri, ns, lane, true, marginal);
 }
 
+// ---- split pipeline: task records ------------------------------------------------------------------------------------
+// One record per atom that has to be integrated (fp32 Lee-Richards, <= 96 neighbours), written by k_integrate:
+//   TodoHeader | marginal bits (ceil(ns / 32) words, padded to 16 B) | partial sums (one double per chunk) |
+//   prepared records {dz, R, dxy, beta} (16 B each, z-sorted) | sorted positions of the neighbours (for the fp64 redo)
+struct alignas(16) TodoHeader {
+    int pos, nn, has_marginal, pad0;
+    double Ri, x, y, z;
+    double extra;       // exposed angle (radians) of the marginal slices, from the fp64 redo task; 0 if there are none
+    int pad[2];
+};
+static_assert(sizeof(TodoHeader) == 64, "TodoHeader layout");
+
+struct TodoLayout {
+    unsigned marginal, partial, recs, gpos, bytes;   // byte offsets inside a record
+};
+__host__ __device__ inline TodoLayout todo_layout(int ns, int nn)
+{
+    TodoLayout L;
+    L.marginal = (unsigned)sizeof(TodoHeader);
+    L.partial = L.marginal + (((unsigned)(ns + 31) / 32 * 4 + 15) & ~15u);
+    L.recs = L.partial + (((unsigned)lr_n_chunks(ns) * 8 + 15) & ~15u);
+    L.gpos = L.recs + (unsigned)nn * 16;
+    L.bytes = (L.gpos + (unsigned)nn * 4 + 15) & ~15u;
+    return L;
+}
+
+// the epilogue of every path: one area to the caller's array (and its mirrors / owner, see IntegrateArgs)
+__device__ __forceinline__ void write_area(const Workspace &ws, const IntegrateArgs &args, int pos, double area)
+{
+    const int i = ws.perm[pos];
+    const int idx = args.sorted_output ? pos : i;
+    if (args.owner_slice > 0) {
+        args.peer_out[idx / args.owner_slice][idx] = area;                     // to the GPU that owns this part of the result
+    } else {
+        args.out[idx] = area;
+        for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
+    }
+}
+
+// k_integrate, atom not certified: hand it over to k_slices.  recs: prepared records in the warp's shared memory; side[0..31]:
+// marginal bits; cidx: candidate indices of the gather (tile indices when staged, see lr_redo_exact); pw: the fill's run table.
+// Returns false when the pool is full (the caller then integrates the atom itself).
+__device__ __forceinline__ bool lr_emit_task(const IntegrateArgs &args, const Rec4<float> *recs, const int *side, const int *cidx,
+                                             int pw, int nn, const Self &s, int pos, int lane)
+{
+    const int ns = args.resolution;
+    const TodoLayout L = todo_layout(ns, nn);
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd(&args.todo_ctl->pool_head, (unsigned long long)L.bytes);
+    off = __shfl_sync(kFull, off, 0);
+    if (off + L.bytes > args.todo_cap) return false;
+    unsigned char *rec = args.todo_pool + off;
+    const int words = (ns + 31) / 32;
+    const unsigned mbits = lane < words && ns <= 1024 ? (unsigned)side[lane] : 0u;
+    const bool any_marginal = __any_sync(kFull, mbits != 0u);
+    if (lane == 0) {
+        TodoHeader h;
+        h.pos = pos; h.nn = nn; h.has_marginal = any_marginal ? 1 : 0; h.pad0 = 0;
+        h.Ri = s.R; h.x = s.x; h.y = s.y; h.z = s.z;
+        h.extra = 0.0;
+        h.pad[0] = h.pad[1] = 0;
+        *reinterpret_cast<TodoHeader *>(rec) = h;
+    }
+    if (lane < ((words + 3) & ~3)) reinterpret_cast<unsigned *>(rec + L.marginal)[lane] = mbits;
+    const bool staged = __shfl_sync(kFull, pw, kWStaged) != 0;
+    for (int j0 = 0; j0 < nn; j0 += 32) {
+        const int j = j0 + lane;
+        const int c = j < nn ? cidx[j] : 0;
+        int r = 0;
+#pragma unroll
+        for (int q = 1; q < 9; ++q) r += c >= __shfl_sync(kFull, pw, kWOff + q) ? 1 : 0;   // runs are laid out in order
+        const int p = __shfl_sync(kFull, pw, kWBegin + r) + (c - __shfl_sync(kFull, pw, kWOff + r));
+        if (j < nn) {
+            reinterpret_cast<int *>(rec + L.gpos)[j] = staged ? p : c;
+            reinterpret_cast<Rec4<float> *>(rec + L.recs)[j] = recs[j];
+        }
+    }
+    __threadfence();                                       // the record is complete before it becomes visible in the list
+    __syncwarp();
+    if (lane == 0) {
+        args.todo_list[atomicAdd(&args.todo_ctl->n_todo, 1)] = off;
+        if (any_marginal) args.todo_list[args.todo_redo_base + atomicAdd(&args.todo_ctl->n_redo, 1)] = off;
+    }
+    return true;
+}
+
 template <int ALG, typename T, bool FAST>
 __device__ __forceinline__ bool finish_atom(const Workspace &ws, const IntegrateArgs &args, const WarpMem<ALG, T> &wm,
                                             const double4 *cand_base, const Self &s, int nn, int cap, int pos,
@@ -1026,17 +1130,19 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
                     side[lane] = 0;
                     side[32 + lane] = pw;
                     lr_prepare_sorted<3>(recs, nn, lane);           // instruction-cache sensitive (ncu: no_instruction stalls
-#ifdef FSB200_DBG_NO_PREPASS
-                    if (false) {
-#else
                     if (can_redo) {                                 // with K = 1, 2, 3 side by side)
-#endif
                         // thick slices (low resolution) need a wider band: an angular error e costs delta Ri e of area.  Floor
                         // 3e-6 (1M atoms, PDB-rounded, n = 100: 4.5e-4 -> 7e-5 A^2), growing with (delta Ri)^2 to 2.4e-5 at n = 5
                         const float dR = (float)(2.0 * s.R * s.R / args.resolution);
                         lr_mark_marginal(recs, side, nn, (float)s.R, args.resolution, fmaxf(FSB200_NEAR_FLOOR, FSB200_NEAR_SCALE * dR * dR), lane);
                     }
-                    area = lr_atom_fastk<3>(recs, arcs, side, nn, s.R, args.resolution, lane, can_redo);
+                    if (args.todo_pool != nullptr && lr_emit_task(args, recs, side, wm.cidx, pw, nn, s, pos, lane)) {
+                        if (lane == 0 && args.nn_out) args.nn_out[ws.perm[pos]] = nn;
+                        return false;                               // k_slices (and k_redo) finish this atom
+                    }
+                    if (lane == 0 && args.todo_pool != nullptr) atomicAdd(&args.todo_ctl->n_inline, 1);
+                    area = lr_atom_fastk<3>(recs, arcs, can_redo ? reinterpret_cast<const unsigned *>(side) : nullptr, nn, s.R,
+                                            args.resolution, lane);
                     if (can_redo && __any_sync(kFull, side[lane] != 0)) {
                         if (lane == 0) atomicAdd(ws.counters + kCtrMarginal, 1);
                         area += lr_redo_exact(ws.atoms, reinterpret_cast<unsigned char *>(wm.recs), wm.cidx, nn, s.x, s.y, s.z,
@@ -1055,15 +1161,8 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
         }
     }
     if (lane == 0) {
-        const int i = ws.perm[pos];
-        const int idx = args.sorted_output ? pos : i;
-        if (args.owner_slice > 0) {
-            args.peer_out[idx / args.owner_slice][idx] = area;                     // to the GPU that owns this part of the result
-        } else {
-            args.out[idx] = area;
-            for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
-        }
-        if (args.nn_out) args.nn_out[i] = nn | (certified ? (1 << 30) : 0);
+        write_area(ws, args, pos, area);
+        if (args.nn_out) args.nn_out[ws.perm[pos]] = nn | (certified ? (1 << 30) : 0);
     }
     return certified;
 }
@@ -1411,6 +1510,102 @@ __global__ void __launch_bounds__(128) k_overflow(Workspace ws, IntegrateArgs ar
     }
 }
 
+// ---- split pipeline, second kernel: the slice loop and nothing else ---------------------------------------------------
+// Persistent; a warp takes tasks from one queue.  The first n_redo tasks are the fp64 redos of the atoms with marginal
+// slices (long, rare: started first so that they overlap with everything else); every other task is a (task record, chunk
+// of slices) pair: the warp loads its K records straight into registers (coalesced 16-B loads from the pool, L2-resident),
+// runs the chunk and stores the partial sum.  Nothing is synchronised between tasks; k_finish adds the partials of an atom
+// IN CHUNK ORDER after this kernel (bit-reproducible).  Why a kernel of its own: the hot loop of the fused kernel shared
+// the SM's instruction caches (L0 ~6 KB per scheduler, L1.5 32 KB) with gather, certificate, ring and sort code of other
+// warps; ncu (round 2): 29 % of all warp stall samples were `no_instruction`, 52 % inside the certificate, and every 2 KB
+// of added per-atom code cost 10 % of kernel time.  Here every warp of the SM runs the same ~6 KB, and the unit of work is
+// a few microseconds, so the tail of the launch is short without any ordering tricks.
+constexpr int kSliceWarps = 8;
+
+__device__ __noinline__ void redo_task(const Workspace &ws, const IntegrateArgs &args, unsigned char *rec, unsigned char *mem, int lane)
+{
+    Rec4<double> *recs = reinterpret_cast<Rec4<double> *>(mem);
+    Arc<double> *arcs = reinterpret_cast<Arc<double> *>(mem + (size_t)kRedoMaxNeighbours * sizeof(Rec4<double>));
+    TodoHeader *h = reinterpret_cast<TodoHeader *>(rec);
+    const int ns = args.resolution, nn = h->nn;
+    const TodoLayout L = todo_layout(ns, nn);
+    const int *gpos = reinterpret_cast<const int *>(rec + L.gpos);
+    const unsigned marginal = lane < (ns + 31) / 32 ? reinterpret_cast<const unsigned *>(rec + L.marginal)[lane] : 0u;
+    for (int j = lane; j < nn; j += 32) {                  // fp64 records in the atom-local frame, as the gather forms them
+        const double4 q = ws.atoms[gpos[j]];
+        const double dx = q.x - h->x, dy = q.y - h->y, dz = q.z - h->z;
+        Rec4<double> o;
+        o.a = dz;
+        o.b = q.w;
+        o.c = sqrt(dx * dx + dy * dy);
+        o.d = atan2(dy, dx) + 3.141592653589793;
+        recs[j] = o;
+    }
+    __syncwarp();
+    const double extra = lr_atom<double>(recs, arcs, nn, h->Ri, ns, lane, true, marginal);
+    if (lane == 0) {
+        h->extra = extra;
+        atomicAdd(ws.counters + kCtrMarginal, 1);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSliceWarps * 32, FSB200_SLICE_CTAS) k_slices(Workspace ws, IntegrateArgs args)
+{
+    __shared__ __align__(16) unsigned char mem_all[kSliceWarps][kRedoMaxNeighbours * (sizeof(Rec4<double>) + sizeof(Arc<double>))];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KeyArc *arcs = reinterpret_cast<KeyArc *>(mem_all[warp]);
+    TodoCtl *ctl = args.todo_ctl;
+    const int ns = args.resolution, S = lr_chunk_slices(ns), n_chunks = lr_n_chunks(ns);
+    const int n_redo = ctl->n_redo;                                      // k_integrate has finished: final
+    const long long n_tasks = (long long)n_redo + (long long)ctl->n_todo * n_chunks;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&ctl->task_head, 1);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= n_tasks) break;
+        if (t < n_redo) {
+            redo_task(ws, args, args.todo_pool + args.todo_list[args.todo_redo_base + t], mem_all[warp], lane);
+            continue;
+        }
+        t -= n_redo;
+        const int a = t / n_chunks, c = t - a * n_chunks;
+        unsigned char *rec = args.todo_pool + args.todo_list[a];
+        const TodoHeader *h = reinterpret_cast<const TodoHeader *>(rec);
+        const int nn = h->nn;
+        const double Ri = h->Ri;
+        const TodoLayout L = todo_layout(ns, nn);
+        const Rec4<float> *recs = reinterpret_cast<const Rec4<float> *>(rec + L.recs);
+        Rec4<float> r[kLrK];
+        bool v[kLrK];
+#pragma unroll
+        for (int k = 0; k < kLrK; ++k) {
+            v[k] = lane + 32 * k < nn;
+            r[k] = recs[v[k] ? lane + 32 * k : 0];
+        }
+        const unsigned *marginal = h->has_marginal ? reinterpret_cast<const unsigned *>(rec + L.marginal) : nullptr;
+        const double part = lr_slices_chunk<kLrK>(r, v, arcs, marginal, nn, Ri, ns, c * S, min(c * S + S, ns), lane);
+        if (lane == 0) reinterpret_cast<double *>(rec + L.partial)[c] = part;
+        __syncwarp();
+    }
+}
+
+// ---- split pipeline, last kernel: one thread per task record adds the chunks in order and writes the area ---------------
+__global__ void __launch_bounds__(256) k_finish(Workspace ws, IntegrateArgs args)
+{
+    const int n_todo = args.todo_ctl->n_todo, ns = args.resolution, n_chunks = lr_n_chunks(ns);
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_todo; a += gridDim.x * blockDim.x) {
+        const unsigned char *rec = args.todo_pool + args.todo_list[a];
+        const TodoHeader *h = reinterpret_cast<const TodoHeader *>(rec);
+        const double *partial = reinterpret_cast<const double *>(rec + todo_layout(ns, h->nn).partial);
+        double sum = 0.0;
+        for (int k = 0; k < n_chunks; ++k) sum += partial[k];
+        const double Ri = h->Ri, delta = 2.0 * Ri / ns;
+        // fp32 path: sectors -> radians (2 pi / 32); the fp64 redo returns delta * Ri * angle itself
+        write_area(ws, args, h->pos, delta * Ri * sum * 0.19634954084936207 + h->extra);
+    }
+}
+
 template <int ALG, typename T> size_t cta_smem_bytes()
 {
     return (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)kWarpsPerCta * WarpLayout<ALG, T>::bytes(kNbCap);
@@ -1436,9 +1631,28 @@ int integrate_grid_ctas(int alg, int precision, int device)
     return precision == 0 ? configure_and_occupancy<1, float>(device) : configure_and_occupancy<1, double>(device);
 }
 
+size_t todo_pool_bytes_per_atom(int resolution) { return todo_layout(resolution, 96).bytes; }
+
 int launch_integrate(const Workspace &ws, const IntegrateArgs &args, cudaStream_t stream)
 {
     const int grid = args.grid_ctas;
+    if (args.alg == 0 && args.precision == 0 && args.todo_pool != nullptr) {
+        // split pipeline: prepare -> slices -> marginal slices; all three grids are persistent, sized for the device, and
+        // read their queue lengths from device memory, so nothing comes back to the host in between
+        static int slices_ctas = 0, sms = 0;
+        if (slices_ctas == 0) {
+            int dev = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_slices, kSliceWarps * 32, 0);
+            slices_ctas = (per_sm < 1 ? 1 : per_sm) * sms;
+        }
+        cudaMemsetAsync(args.todo_ctl, 0, sizeof(TodoCtl), stream);
+        k_integrate<0, float><<<grid, kCtaThreads, cta_smem_bytes<0, float>(), stream>>>(ws, args);
+        k_slices<<<slices_ctas, kSliceWarps * 32, 0, stream>>>(ws, args);
+        k_finish<<<sms, 256, 0, stream>>>(ws, args);
+        return 3;
+    }
     if (args.alg == 0) {
         if (args.precision == 0)
             k_integrate<0, float><<<grid, kCtaThreads, cta_smem_bytes<0, float>(), stream>>>(ws, args);

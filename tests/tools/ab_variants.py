@@ -19,16 +19,18 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = {
     "product": [],
-    "no_exact_slices": ["FSB200_EXACT_SLICES=0"],
-    "dbg_no_bittest": ["FSB200_DBG_NO_BITTEST=1"],     # timing only (marginal slices are counted twice)
-    "dbg_no_prepass": ["FSB200_DBG_NO_PREPASS=1"],     # timing only (nothing is marked)
-    "dbg_neither": ["FSB200_DBG_NO_PREPASS=1", "FSB200_DBG_NO_BITTEST=1"],
+    "slices5": ["FSB200_SLICE_CTAS=5"],
+    "slices6": ["FSB200_SLICE_CTAS=6"],
+    "chunk16": ["FSB200_CHUNK=16"],
+    "slices6_chunk16": ["FSB200_SLICE_CTAS=6", "FSB200_CHUNK=16"],
+    "slices6_chunk4": ["FSB200_SLICE_CTAS=6", "FSB200_CHUNK=4"],
 }
 TAIL_VARIANTS = ()   # these also measure the 1M-atom PDB-rounded error tail
 
 
 def lib_path(name):
-    return os.path.join(ROOT, "freesasa_b200", "csrc", "libfsb200.so" if name == "product" else f"libfsb200_{name}.so")
+    own = [d for d in VARIANTS[name] if not d.startswith("env:")]
+    return os.path.join(ROOT, "freesasa_b200", "csrc", f"libfsb200_{name}.so" if own else "libfsb200.so")
 
 
 def build():
@@ -36,7 +38,7 @@ def build():
 
     b.build_library()
     for name, defs in VARIANTS.items():
-        if name == "product":
+        if not [d for d in defs if not d.startswith("env:")]:
             continue
         replace = {}
         for d in [d for d in defs if d.startswith("@")]:
@@ -46,7 +48,7 @@ def build():
                 f.write(subprocess.run(["git", "show", f"{rev}:freesasa_b200/csrc/{src}"], cwd=ROOT, check=True,
                                        capture_output=True, text=True).stdout)
             replace[src] = old
-        print(b.build_variant(name, [d for d in defs if not d.startswith("@")], replace=replace), flush=True)
+        print(b.build_variant(name, [d for d in defs if d[0] not in "@e" or not (d.startswith("@") or d.startswith("env:"))], replace=replace), flush=True)
 
 
 def measure():
@@ -106,6 +108,10 @@ def run(names):
     results = {}
     for name in names:
         env = dict(os.environ, FSB200_ENGINE_LIB=lib_path(name))
+        for d in VARIANTS[name]:
+            if d.startswith("env:"):
+                k, v = d[4:].split("=", 1)
+                env[k] = v
         if name in TAIL_VARIANTS:
             env["AB_TAIL"] = "1"
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "--measure"], env=env, capture_output=True, text=True, timeout=900)
