@@ -322,6 +322,13 @@ def trim() -> int:
     return int(_engine_lib().fsb200_trim())
 
 
+def _stream_handle(torch_stream) -> int:
+    """cudaStream_t of a torch stream for the C ABI, where NULL means "the context's own stream": torch's legacy default
+    stream has the handle 0, so it is passed as cudaStreamLegacy (1) — otherwise work queued through torch on the default
+    stream and the engine's kernels would run on two unrelated streams."""
+    return int(torch_stream.cuda_stream) or 1
+
+
 class IpcBuffer:
     """A device buffer other processes can map (CUDA IPC): the symmetric output / flag buffers of the fused all-gather.
     ``handle`` (64 bytes) is what a peer passes to ``IpcBuffer.open``."""
@@ -454,7 +461,7 @@ class Engine:
         if out is None:
             out = torch.zeros(n, dtype=torch.float64, device=d_radii.device)
         if stream is None:
-            stream = torch.cuda.current_stream(d_radii.device).cuda_stream
+            stream = _stream_handle(torch.cuda.current_stream(d_radii.device))
         n_struct, off_p = 1, None
         if offsets is not None:
             off = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -476,7 +483,7 @@ class Engine:
         if out is None:
             out = torch.zeros(n, dtype=torch.float64, device=d_radii.device)
         if stream is None:
-            stream = torch.cuda.current_stream(d_radii.device).cuda_stream
+            stream = _stream_handle(torch.cuda.current_stream(d_radii.device))
         n_struct, off_p = 1, None
         if offsets is not None:
             off = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -502,7 +509,7 @@ class Engine:
         import torch
 
         if stream is None:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            stream = _stream_handle(torch.cuda.current_stream(self.device))
         arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in flag_pointers])
         self._check(self._L.fsb200_ctx_peer_barrier(self._ctx, int(rank), int(world), arr, ctypes.c_void_p(stream)),
                     "fsb200_ctx_peer_barrier")
@@ -520,7 +527,7 @@ class Engine:
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=d_sorted.device)
         if stream is None:
-            stream = torch.cuda.current_stream(d_sorted.device).cuda_stream
+            stream = _stream_handle(torch.cuda.current_stream(d_sorted.device))
         self._check(self._L.fsb200_ctx_unpermute(self._ctx, d_sorted.data_ptr(), out.data_ptr(), n, ctypes.c_void_p(stream)),
                     "fsb200_ctx_unpermute")
         return out

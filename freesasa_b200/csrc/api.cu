@@ -1468,6 +1468,24 @@ int multi_batch(int alg, int n_struct, const int *n_atoms, const double *const *
     return FSB200_SUCCESS;
 }
 
+// the one-device case of fsb200_calc_multi: the ordinary batch call, timed like the others
+int single_device(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
+                  double *const *sasa, double probe, int resolution)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = fsb200_calc_batch(alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
+    fsb200_multi_stats ms{};
+    ms.n_devices = 1;
+    ms.n_structures = n_struct;
+    for (int k = 0; k < n_struct; ++k) ms.n_atoms += n_atoms[k] > 0 ? n_atoms[k] : 0;
+    ms.total_ms = ms.compute_ms = (float)ms_since(t0);
+    ms.device_ms[0] = g_last_stats.device_ms;
+    ms.integrate_ms[0] = g_last_stats.integrate_ms;
+    std::lock_guard<std::mutex> g(g_multi_stats_lock);
+    g_multi_stats = ms;
+    return rc;
+}
+
 }  // namespace
 
 int fsb200_calc_multi(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
@@ -1492,13 +1510,13 @@ int fsb200_calc_multi(int alg, int n_struct, const int *n_atoms, const double *c
             // too small to be worth a second GPU: one device, the ordinary path
             if (n_devices == 1 || n_atoms[0] < 16384 * n_devices) {
                 DeviceGuard guard(devs[0]);
-                return fsb200_calc_batch(alg, 1, n_atoms, xyz, radii, sasa, probe, resolution);
+                return single_device(alg, 1, n_atoms, xyz, radii, sasa, probe, resolution);
             }
             return multi_replicated(alg, n_atoms[0], xyz[0], radii[0], sasa[0], probe, resolution, devs);
         }
         if (n_devices == 1) {
             DeviceGuard guard(devs[0]);
-            return fsb200_calc_batch(alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
+            return single_device(alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution);
         }
         for (int k = 0; k < n_struct; ++k)
             if (n_atoms[k] <= 0 || !xyz[k] || !radii[k] || !sasa[k]) return fail("structure %d is empty or has a null array", k);

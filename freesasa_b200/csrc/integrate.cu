@@ -88,6 +88,9 @@ __device__ __forceinline__ unsigned lanemask_lt()
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+// the same mask from the lane index with two ALU instructions: under register pressure the compiler re-reads the special
+// register at every use (S2R, ~20 cycles; ncu round 2: 12 M of the slice kernel's 228 M warp instructions)
+__device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
 // ---- description of a staged fill (Slot::w below), one word per lane -------------------------------------
 // payload word indices: runs r = 0..8 of the 27-cell neighbourhood, then the scalars
@@ -164,7 +167,7 @@ __device__ __forceinline__ int gather_run(const double4 *base, int cnt, int skip
         }
         const unsigned m = __ballot_sync(kFull, hit);
         if (hit) {
-            const int slot = nn + __popc(m & lanemask_lt());
+            const int slot = nn + __popc(m & lanemask_lt(lane));
             if (slot < cap) {
                 Rec4<T> r;
                 r.a = (T)dx; r.b = (T)dy; r.c = (T)dz;
@@ -610,7 +613,7 @@ __device__ __forceinline__ double lr_slices_chunk(const Rec4<float> (&r)[K], con
 {
     const float Ri = (float)Ri_d;
     const double delta = 2.0 * Ri_d / ns;
-    const unsigned lt = lanemask_lt();
+    const unsigned lt = lanemask_lt(lane);
     double acc = 0.0;                                      // exposed angle in sectors
 
     for (int s = s_begin; s < s_end; ++s) {
@@ -1231,11 +1234,11 @@ __device__ __forceinline__ int ld_acquire(int *p)
     asm volatile("atom.acquire.cta.shared::cta.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(smem_addr(p)) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v)
+__device__ __forceinline__ int st_release(int *p, int v)   // returns the previous value (callers ignore it)
 {
     int old;
     asm volatile("atom.release.cta.shared::cta.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr(p)), "r"(v) : "memory");
-    (void)old;
+    return old;
 }
 __device__ __forceinline__ int cas_acq_rel(int *p, int expected, int desired)
 {
@@ -1251,7 +1254,7 @@ __device__ __forceinline__ int add_acq_rel(int *p, int v)
 }
 #else
 __device__ __forceinline__ int ld_acquire(int *p) { return *reinterpret_cast<volatile int *>(p); }
-__device__ __forceinline__ void st_release(int *p, int v) { __threadfence_block(); *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ int st_release(int *p, int v) { __threadfence_block(); *reinterpret_cast<volatile int *>(p) = v; return 0; }
 __device__ __forceinline__ int cas_acq_rel(int *p, int expected, int desired) { return atomicCAS(p, expected, desired); }
 __device__ __forceinline__ int add_acq_rel(int *p, int v) { __threadfence_block(); return atomicAdd(p, v); }
 #endif

@@ -115,12 +115,15 @@ def gather_after_enqueue(engine, enqueue: Callable[[], "object"], gather: Callab
 
 
 class PeerGather:
-    """The all-gather of per-atom areas WITHOUT a collective call: every rank owns one symmetric output buffer (CUDA IPC),
-    maps the buffers of all peers, and its integration kernel stores each area into ALL of them from its epilogue (8 B per
-    atom and peer over NVLink).  A step is
-        ready barrier -> calc_device_async (peer stores) -> done barrier -> finish
-    where the barriers are one-warp kernels flipping epoch flags in peer memory (fsb200_ctx_peer_barrier): no NCCL call and
-    no host synchronisation between the kernel and the exchange.  torch.distributed is used ONCE, at construction, to
+    """The all-gather of per-atom areas WITHOUT a collective call: every rank owns symmetric output buffers (CUDA IPC),
+    maps the buffers of all peers, and its integration kernels store each area into ALL of them (8 B per atom and peer over
+    NVLink).  A step is
+        calc_device_async (peer stores) -> done barrier -> finish
+    where the barrier is a one-warp kernel flipping epoch flags in peer memory (fsb200_ctx_peer_barrier): no NCCL call and
+    no host synchronisation between the kernels and the exchange.  Two buffers alternate from step to step, which is what
+    makes a second ("everybody has consumed the previous result") barrier unnecessary: a rank can only be writing step
+    k + 2 into the buffer of step k after every rank has passed the barrier of step k + 1, i.e. after every rank has begun
+    step k + 1 and is therefore done with the result of step k.  torch.distributed is used ONCE, at construction, to
     exchange the 64-byte IPC handles."""
 
     def __init__(self, engine, n_total: int, rank: int, world: int, slot=None):
@@ -135,22 +138,24 @@ class PeerGather:
         self.engine, self.rank, self.world, self.n = engine, rank, world, int(n_total)
         self.slot = slot
         dev = engine.device
-        self.mine = IpcBuffer(dev, 8 * self.n)
+        self.mine = [IpcBuffer(dev, 8 * self.n) for _ in range(2)]
         self.flags = IpcBuffer(dev, 4 * 64)
         handles = [None] * world
-        dist.all_gather_object(handles, (self.mine.handle, self.flags.handle))
-        self.peers, self.peer_flags = [], []
-        for r, (h_out, h_flag) in enumerate(handles):
+        dist.all_gather_object(handles, (self.mine[0].handle, self.mine[1].handle, self.flags.handle))
+        self.peers, self.peer_flags = [[], []], []
+        for r, (h0, h1, h_flag) in enumerate(handles):
             if r == rank:
-                self.peers.append(self.mine)
+                self.peers[0].append(self.mine[0])
+                self.peers[1].append(self.mine[1])
                 self.peer_flags.append(self.flags)
             else:
-                self.peers.append(IpcBuffer.open(dev, h_out, 8 * self.n))
+                self.peers[0].append(IpcBuffer.open(dev, h0, 8 * self.n))
+                self.peers[1].append(IpcBuffer.open(dev, h1, 8 * self.n))
                 self.peer_flags.append(IpcBuffer.open(dev, h_flag, 4 * 64))
-        self.out = self.mine.tensor(torch.float64, self.n)
-        off = 8 * int(slot[0]) if slot else 0
-        self.window = self.out[slot[0]:slot[0] + slot[1]] if slot else self.out
-        engine.set_peer_outputs([p.ptr + off for r, p in enumerate(self.peers) if r != rank])
+        self.outs = [m.tensor(torch.float64, self.n) for m in self.mine]
+        self.windows = [o[slot[0]:slot[0] + slot[1]] if slot else o for o in self.outs]
+        self.parity = 0
+        self.out = self.outs[0]
         dist.barrier()
 
     def barrier(self):
@@ -158,10 +163,13 @@ class PeerGather:
 
     def step(self, enqueue: Callable[["object"], "object"]):
         """enqueue(out) must call engine.calc_device_async(..., out=out).  Returns the complete result (this rank's
-        symmetric buffer) after the one synchronisation."""
-        self.barrier()          # every rank has consumed the previous result: its buffer may be overwritten
-        enqueue(self.window)
-        self.barrier()          # every rank's kernel — and with it every peer store into my buffer — is complete
+        symmetric buffer of this step; valid until the step after the next) after the one synchronisation."""
+        k = self.parity
+        self.parity ^= 1
+        off = 8 * int(self.slot[0]) if self.slot else 0
+        self.engine.set_peer_outputs([p.ptr + off for r, p in enumerate(self.peers[k]) if r != self.rank])
+        enqueue(self.windows[k])
+        self.barrier()          # every rank's kernels — and with them every peer store into my buffer — are complete
         rc = self.engine.finish()
         if rc != 0:             # second pass ran after the barrier: agree on completion once more
             import torch
@@ -169,11 +177,15 @@ class PeerGather:
             self.barrier()
             torch.cuda.current_stream().synchronize()
         self.engine.peer_barrier_status()
+        self.out = self.outs[k]
         return self.out
 
     def close(self):
         self.engine.set_peer_outputs([])
-        for r, (p, f) in enumerate(zip(self.peers, self.peer_flags)):
+        for k in range(2):
+            for r, p in enumerate(self.peers[k]):
+                if r != self.rank:
+                    p.close()
+        for r, f in enumerate(self.peer_flags):
             if r != self.rank:
-                p.close()
                 f.close()

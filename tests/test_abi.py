@@ -143,3 +143,23 @@ def test_public_headers_compile_as_c99_and_cxx14(tmp_path):
                     "-I", inc, "-fsyntax-only", c], check=True)
     subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", inc,
                     "-fsyntax-only", cxx], check=True)
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_gpu():
+    """fsb200_calc_multi / _lr_multi / the two-half device call: no silent fallback when no sm_100 device is visible, and the
+    bookkeeping entry points (trim, statistics) work without one."""
+    import numpy as np
+
+    if fs.available():
+        pytest.skip("a B200 is visible")
+    x, r = fs.workloads.globule(50)
+    with pytest.raises(RuntimeError, match="no sm_100 device|no CUDA|CPU path"):
+        fs.calc_multi(fs.LEE_RICHARDS, [(x, r)], 1.4, 20, n_devices=2)
+    with pytest.raises(RuntimeError):
+        fs.calc_multi(fs.LEE_RICHARDS, [(x, r), (x, r)], 1.4, 20, n_devices=0)
+    assert fs.trim() == 0
+    st = fs.multi_stats()
+    assert st["n_devices"] == 0 and st["total_ms"] == 0.0
+    with pytest.raises(RuntimeError):
+        fs.IpcBuffer(0, 1024)
+    assert isinstance(np.asarray(fs.device_count()).item(), int)

@@ -74,6 +74,62 @@ def _worker(rank, world, port, tmp):
 
     got = parallel.calc_replicated_sharded(len(r), compute_shard, unpermute)
     ok &= np.array_equal(got.numpy(), full)
+
+    # ---- the two-half step: kernels enqueued, collective queued behind them, ONE synchronisation; when the engine reports
+    # a second pass (results completed after the collective had been queued) the collective must be issued again
+    class FakeEngine:
+        """Plays fsb200_ctx_calc_device_async / fsb200_ctx_finish: the first `late` shards are only complete after finish()."""
+
+        def __init__(self, late):
+            self.late, self.calls = late, 0
+
+        def enqueue(self):
+            b, e = parallel.shard_bounds(len(r), world)[rank]
+            self.buf = torch.zeros(len(r), dtype=torch.float64)
+            self.buf[b:e] = torch.from_numpy(full[perm][b:e])
+            if self.late:
+                self.hidden = self.buf[b].clone()
+                self.buf[b] = -1.0          # not there yet
+            return self.buf
+
+        def finish(self):
+            if self.late:
+                b, _ = parallel.shard_bounds(len(r), world)[rank]
+                self.buf[b] = self.hidden   # the second pass completes it
+                self.late = False
+                return 1                     # FSB200_SECOND_PASS
+            return 0
+
+    for late in (False, True):
+        eng = FakeEngine(late)
+        bounds = parallel.shard_bounds(len(r), world)
+        width = max(e - b for b, e in bounds)
+        n_gathers = [0]
+
+        def gather(local):
+            n_gathers[0] += 1
+            b, e = bounds[rank]
+            padded = torch.zeros(width, dtype=torch.float64)
+            padded[: e - b] = local[b:e]
+            out = torch.empty(world * width, dtype=torch.float64)
+            dist.all_gather_into_tensor(out, padded)
+            return out
+
+        import sys
+        import types
+
+        fake_cuda = None
+        if late and not torch.cuda.is_available():   # gather_after_enqueue synchronises the current CUDA stream after a redo
+            fake_cuda = torch.cuda.current_stream
+            torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(synchronize=lambda: None)
+        try:
+            g = parallel.gather_after_enqueue(eng, eng.enqueue, gather).view(world, width)
+        finally:
+            if fake_cuda is not None:
+                torch.cuda.current_stream = fake_cuda
+        merged = torch.cat([g[q, : e - b] for q, (b, e) in enumerate(bounds)])
+        ok &= np.array_equal(unpermute(merged).numpy(), full)
+        ok &= n_gathers[0] == (2 if late else 1)
     with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
         f.write("1" if ok else "0")
     dist.destroy_process_group()

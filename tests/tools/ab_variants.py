@@ -19,13 +19,10 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = {
     "product": [],
-    "slices5": ["FSB200_SLICE_CTAS=5"],
-    "slices6": ["FSB200_SLICE_CTAS=6"],
-    "chunk16": ["FSB200_CHUNK=16"],
-    "slices6_chunk16": ["FSB200_SLICE_CTAS=6", "FSB200_CHUNK=16"],
-    "slices6_chunk4": ["FSB200_SLICE_CTAS=6", "FSB200_CHUNK=4"],
+    "fused": ["env:FSB200_PIPELINE=fused"],            # the same library, everything inside k_integrate (round 1's layout)
+    "r1_kernel": ["@integrate.cu=f4eaa4c"],          # integrate.cu of the round-1 commit, against today's api.cu / cells.cu
 }
-TAIL_VARIANTS = ()   # these also measure the 1M-atom PDB-rounded error tail
+TAIL_VARIANTS = ("product",)   # these also measure the 1M-atom PDB-rounded error tail
 
 
 def lib_path(name):
