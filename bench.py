@@ -9,10 +9,13 @@ n_slices=100, 100k-atom synthetic globule; max |dSASA| vs the reference).
 A "step" is one pass of the hot path (cell list build + integration of every atom) over one structure per GPU.
 N=1: config C2.  N>1 (launched by torch.distributed.run, one rank per GPU): every rank integrates its own 100k-atom
 structure (weak scaling: work per GPU fixed) and the step ends with the all-gather of the per-atom SASA of all ranks;
-value = atoms of all ranks / max-over-ranks time.  The all-gather is FUSED into the integration kernel: every rank's
-kernel stores each area into the symmetric result buffer of every rank (peer memory over NVLink, CUDA IPC), closed by a
-one-warp flag barrier in peer memory — no NCCL call and no host synchronisation between the kernel and the exchange
-(`--collective nccl` runs the plain variant: kernels enqueued, one ncclAllGather queued behind them, one synchronisation).
+value = atoms of all ranks / max-over-ranks time.  Two implementations of that all-gather, neither with a host round trip
+between the kernels and the exchange (round 1 synchronised first, which held 8-GPU efficiency at 0.87):
+`--collective nccl` (default): kernels enqueued (fsb200_ctx_calc_device_async), ONE ncclAllGather queued behind them on the same
+stream, fsb200_ctx_finish is the only synchronisation; `--collective peer`: no collective call at all — the kernels store every
+non-zero area into the symmetric result buffer of every rank themselves (peer memory over NVLink, CUDA IPC; the buried
+atoms' zeros are memset by each owner), closed by a one-warp flag barrier in peer memory.  The fused variant is measured
+and tested but slower on this workload (the exchange is 8 B per atom once per 0.5 ms of compute): NCCL is the default.
 
 Reported numbers
   value    atoms/s with the inputs already resident in HBM; device time from CUDA events on the stream
@@ -320,8 +323,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--alg", default="lr", choices=["lr", "sr"], help="lr: config C2 (the headline metric); sr: config C3")
-    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
-                    help="N>1: peer = all-gather fused into the kernel (peer stores over NVLink + flag barriers); nccl = ncclAllGather queued behind the kernel")
+    ap.add_argument("--collective", default="nccl", choices=["peer", "nccl"],
+                    help="N>1: nccl = kernels enqueued, ONE ncclAllGather queued behind them, one synchronisation (default: measured "
+                         "faster, 0.590 vs 0.612 ms per step on 2 GPUs, 0.640 vs 0.660 on 8); peer = no collective call: areas stored "
+                         "into every rank's symmetric buffer by the kernels themselves (NVLink peer stores) + one flag barrier")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip ablation / surface workload / C3 / C4 / C5 sections")
     ap.add_argument("--no-certificate", action="store_true",

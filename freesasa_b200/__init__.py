@@ -164,6 +164,7 @@ def _engine_lib():
         L.fsb200_ctx_calc_device_async.argtypes = L.fsb200_ctx_calc_device.argtypes
         L.fsb200_ctx_finish.argtypes = [vp]
         L.fsb200_ctx_set_peer_outputs.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
+        L.fsb200_ctx_set_peer_zero_skipping.argtypes = [vp, ctypes.c_int]
         L.fsb200_ctx_peer_barrier.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), vp]
         L.fsb200_ctx_peer_barrier_status.argtypes = [vp]
         L.fsb200_ctx_generation.restype = ctypes.c_ulonglong
@@ -504,6 +505,9 @@ class Engine:
         """Mirror every area into these device buffers (usually on other GPUs) from the kernel epilogue."""
         arr = (ctypes.c_void_p * max(1, len(pointers)))(*[ctypes.c_void_p(int(p)) for p in pointers])
         self._check(self._L.fsb200_ctx_set_peer_outputs(self._ctx, len(pointers), arr), "fsb200_ctx_set_peer_outputs")
+
+    def set_peer_zero_skipping(self, on: bool):
+        self._check(self._L.fsb200_ctx_set_peer_zero_skipping(self._ctx, 1 if on else 0), "fsb200_ctx_set_peer_zero_skipping")
 
     def peer_barrier(self, rank: int, world: int, flag_pointers: Sequence[int], stream=None):
         import torch

@@ -102,6 +102,7 @@ struct fsb200_ctx {
     int precision = FSB200_FP32;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_upload = nullptr;   // multi-device: "my slice of the inputs is on the device" (created on first use)
     int *h_status = nullptr;  // pinned, kCtrCount ints
     // The cell-list build (3 memsets + 9 kernels) is captured once per distinct Workspace and replayed as ONE
     // CUDA graph launch: the device timeline no longer depends on how fast the host can issue 12 calls
@@ -151,6 +152,7 @@ struct fsb200_ctx {
     // mirrors of the output on other GPUs (fsb200_ctx_set_peer_outputs), applied to device-resident calls
     int barrier_epoch = 0;
     DevBuf<int> barrier_status;   // one int, 0 = fine
+    bool peer_skip_zero = false;   // peers zero their buffers themselves: areas that are exactly 0 are not stored remotely
     int n_peer_out = 0;
     double *peer_out[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -328,9 +330,17 @@ struct CopyJob {
     size_t bytes;
 };
 
+// Worker threads of the multi-device entry point copy with their own core: the pool serialises its jobs (one at a time),
+// which would queue the staging copies of all GPUs behind each other (measured on 8 GPUs: 7.5 ms per device instead of 4).
+thread_local bool g_copy_inline = false;
+
 // all jobs, cut into kCopyPiece pieces, spread over the pool
 void parallel_copy(const std::vector<CopyJob> &jobs)
 {
+    if (g_copy_inline) {
+        for (const CopyJob &j : jobs) std::memcpy(j.dst, j.src, j.bytes);
+        return;
+    }
     struct Piece { unsigned char *d; const unsigned char *s; size_t n; };
     std::vector<Piece> pieces;
     size_t total = 0;
@@ -386,6 +396,7 @@ struct Request {
     int n_peer_out = 0;
     double *const *peer_out = nullptr;
     int owner_slice = 0;     // > 0: results partitioned by caller index over peer_out[] (IntegrateArgs::owner_slice)
+    bool peer_skip_zero = false;
 };
 
 // A call is two halves.  enqueue_pipeline() validates and puts the whole device sequence on the stream — cell-list build
@@ -429,6 +440,7 @@ int enqueue_pipeline(fsb200_ctx *c, const Request &rq)
     ia.n_peer_out = rq.n_peer_out;
     for (int q = 0; q < rq.n_peer_out; ++q) ia.peer_out[q] = rq.peer_out[q];
     ia.owner_slice = rq.owner_slice;
+    ia.peer_skip_zero = rq.peer_skip_zero ? 1 : 0;
     if (rq.alg == FSB200_SHRAKE_RUPLEY) {
         if (ensure_points(c, rq.resolution, st)) return FSB200_FAIL;
         ia.points_f = c->points_f.p;
@@ -786,6 +798,7 @@ void fsb200_ctx_destroy(fsb200_ctx *c)
     for (int k = 0; k < 4; ++k)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -950,6 +963,7 @@ static int device_request(fsb200_ctx *c, Request &rq, int alg, const double *d_x
     // without, a shard writes its range of the SORTED order (gather the ranges, then fsb200_ctx_unpermute)
     rq.n_peer_out = c->n_peer_out;
     rq.peer_out = c->peer_out;
+    rq.peer_skip_zero = c->peer_skip_zero;
     rq.sorted_output = (shard_count > 1 && c->n_peer_out == 0) ? 1 : 0;
     return FSB200_SUCCESS;
 }
@@ -1004,6 +1018,14 @@ int fsb200_ctx_set_peer_outputs(fsb200_ctx *c, int n_peers, double *const *d_pee
         c->peer_out[q] = d_peer_sasa[q];
     }
     c->n_peer_out = n_peers;
+    return FSB200_SUCCESS;
+}
+
+int fsb200_ctx_set_peer_zero_skipping(fsb200_ctx *c, int on)
+{
+    if (!c) return fail("null context");
+    std::lock_guard<std::mutex> g(c->lock);
+    c->peer_skip_zero = on != 0;
     return FSB200_SUCCESS;
 }
 
@@ -1185,7 +1207,12 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
         }
     };
     std::vector<std::thread> helpers;
-    for (int w = 1; w < n_workers; ++w) helpers.emplace_back(work, w);
+    const bool copy_inline = g_copy_inline;
+    for (int w = 1; w < n_workers; ++w)
+        helpers.emplace_back([&work, w, copy_inline] {
+            g_copy_inline = copy_inline;
+            work(w);
+        });
     work(0);
     for (auto &h : helpers) h.join();
     g_last_stats = ctx[0]->stats;   // the last sub-batch of worker 0; totals below
@@ -1245,7 +1272,7 @@ struct HostBarrier {
 fsb200_multi_stats g_multi_stats{};
 std::mutex g_multi_stats_lock;
 
-bool enable_peer(int from, int to)
+bool enable_peer_uncached(int from, int to)
 {
     DeviceGuard guard(from);
     int can = 0;
@@ -1256,6 +1283,20 @@ bool enable_peer(int from, int to)
     const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
     cudaGetLastError();
     return e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+}
+
+bool enable_peer(int from, int to)
+{
+    static std::mutex m;
+    static bool known[FSB200_MAX_DEVICES][FSB200_MAX_DEVICES], ok[FSB200_MAX_DEVICES][FSB200_MAX_DEVICES];
+    std::lock_guard<std::mutex> g(m);
+    if (from < FSB200_MAX_DEVICES && to < FSB200_MAX_DEVICES && known[from][to]) return ok[from][to];
+    const bool result = enable_peer_uncached(from, to);
+    if (from < FSB200_MAX_DEVICES && to < FSB200_MAX_DEVICES) {
+        known[from][to] = true;
+        ok[from][to] = result;
+    }
+    return result;
 }
 
 double ms_since(std::chrono::steady_clock::time_point t0)
@@ -1295,6 +1336,7 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
     auto work = [&](int d) {
         fsb200_ctx *c = ctx[d];
         std::lock_guard<std::mutex> lock(c->lock);
+        g_copy_inline = true;
         cudaSetDevice(c->device);
         cudaStream_t st = c->stream;
         auto check = [&](int r) {
@@ -1313,7 +1355,8 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
             cu(c->in_xyz.ensure(3 * (size_t)n), "cudaMalloc");
             cu(c->in_radii.ensure(n), "cudaMalloc");
             cu(c->out_sasa.ensure(slice), "cudaMalloc");
-            cu(cudaEventCreateWithFlags(&uploaded[d], cudaEventDisableTiming), "cudaEventCreate");
+            if (!c->ev_upload) cu(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming), "cudaEventCreate");
+            uploaded[d] = c->ev_upload;
             if (rc[d] == FSB200_SUCCESS && ensure_stage(c, 32 * (size_t)(cnt > 0 ? cnt : 1) + 8 * (size_t)slice)) check(FSB200_FAIL);
             if (rc[d] == FSB200_SUCCESS && cnt > 0) {
                 check(staged_h2d(c, c->in_xyz.p + 3 * (size_t)a0, xyz + 3 * (size_t)a0, 24 * (size_t)cnt, 0, st));
@@ -1387,13 +1430,8 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
     }
     ms.total_ms = (float)ms_since(t_begin);
     ms.download_ms = ms.total_ms - ms.upload_ms - ms.compute_ms;
-    for (int d = 0; d < N; ++d) {
-        if (uploaded[d]) {
-            DeviceGuard guard(ctx[d]->device);
-            cudaStreamSynchronize(ctx[d]->stream);   // nobody may still be pulling from a context that goes back to the pool
-            cudaEventDestroy(uploaded[d]);
-        }
-    }
+    // (every stream has been synchronised by its own thread after the last peer copy out of any context: run_pipeline and
+    //  the download both end with cudaStreamSynchronize, and all pulls are queued before a device's own kernels)
     for (int d = 0; d < N; ++d) pool_release(ctx[d]);
     {
         std::lock_guard<std::mutex> g(g_multi_stats_lock);
@@ -1433,6 +1471,7 @@ int multi_batch(int alg, int n_struct, const int *n_atoms, const double *const *
         if (idx.empty()) return;
         std::sort(idx.begin(), idx.end());
         Range r("fsb200:multi:batch_share");
+        g_copy_inline = true;
         cudaSetDevice(devs[d]);
         const size_t m = idx.size();
         std::vector<int> cnt(m);
@@ -1454,6 +1493,7 @@ int multi_batch(int alg, int n_struct, const int *n_atoms, const double *const *
         for (int d = 1; d < N; ++d) helpers.emplace_back(work, d);
         const int prev = default_device();
         work(0);
+        g_copy_inline = false;
         if (prev >= 0) cudaSetDevice(prev);
         for (auto &h : helpers) h.join();
     }

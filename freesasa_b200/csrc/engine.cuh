@@ -52,6 +52,9 @@ namespace fsb200 {
 #ifndef FSB200_SLICE_CTAS
 #define FSB200_SLICE_CTAS 4       // CTAs of k_slices per SM the compiler has to make room for (register cap)
 #endif
+#ifndef FSB200_SLICES_K
+#define FSB200_SLICES_K 3          // k_slices: instantiations of the slice loop by record groups: 1 = K 3 only; 2 = K 2 + 3; 3 = K 1 + 2 + 3
+#endif
 #ifndef FSB200_RING_SLOTS
 #define FSB200_RING_SLOTS 2
 #endif
@@ -174,6 +177,7 @@ struct IntegrateArgs {
     // to peer_out[i / owner_slice][i] and nowhere else (multi-GPU C entry point: every GPU ends up holding one contiguous
     // slice of the result, which it downloads over its own PCIe link)
     int owner_slice;
+    int peer_skip_zero;   // the mirrors are zeroed by their owners before the call: an area of exactly 0 is not stored remotely
     // Split pipeline of the fp32 Lee-Richards path (null pool = fused: everything inside k_integrate): k_integrate only
     // gathers, certifies and PREPARES; atoms with exposed surface are written to the pool as task records and integrated by
     // k_slices (chunks of slices from a queue), marginal slices by k_redo.

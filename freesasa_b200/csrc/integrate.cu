@@ -455,34 +455,44 @@ __device__ __forceinline__ double lr_atom_fast(const Rec4<float> *recs, KeyArc *
 // Exactness: a sector counts as covered only if ONE arc contains it entirely (integer sector borders are
 // exact in fp32), so replacing the arcs inside covered sectors by the sectors themselves does not change
 // the union.
+// beta = atan2(dy, dx) + pi in sectors (src/sasa_lr.c:337, hoisted out of the slice loop).  Out of line: atan2f is ~40
+// instructions and would be inlined once per record group.
+__device__ __noinline__ float lr_beta_sectors(float dy, float dx)
+{
+    return (atan2f(dy, dx) + 3.141592653589793f) * 5.092958178940651f;   // sectors per radian
+}
+
 template <int K>
 __device__ __forceinline__ void lr_prepare_sorted(Rec4<float> *recs, int nn, int lane)
 {
-    const float kS = 5.092958178940651f;                   // sectors per radian
-    Rec4<float> o[K];
+    Rec4<float> mine[K];
+    float z[K];
     int rank[K];
 #pragma unroll
     for (int h = 0; h < K; ++h) {
         const int j = lane + 32 * h;
-        rank[h] = -1;
-        if (j < nn) {
-            const Rec4<float> r = recs[j];                 // raw {dx, dy, dz, R}
-            int rk = 0;
-            for (int k = 0; k < nn; ++k) {
-                const float dzk = recs[k].c;               // warp-uniform address: broadcast
-                rk += (dzk < r.c || (dzk == r.c && k < j)) ? 1 : 0;
-            }
-            rank[h] = rk;
-            o[h].a = r.c;
-            o[h].b = r.d;
-            o[h].c = sqrtf(r.a * r.a + r.b * r.b);         // src/nb.c:440
-            o[h].d = (atan2f(r.b, r.a) + 3.141592653589793f) * kS;   // beta (src/sasa_lr.c:337), hoisted, in sectors
-        }
+        mine[h] = recs[j < nn ? j : 0];                    // raw {dx, dy, dz, R}
+        z[h] = j < nn ? mine[h].c : 3.0e38f;
+        rank[h] = 0;
+    }
+    // rank of each of my records among all dz (ties by index): ONE pass over the list, every value broadcast once
+#pragma unroll 1
+    for (int k = 0; k < nn; ++k) {
+        const float dzk = recs[k].c;                       // warp-uniform address: broadcast
+#pragma unroll
+        for (int h = 0; h < K; ++h) rank[h] += (dzk < z[h] || (dzk == z[h] && k < lane + 32 * h)) ? 1 : 0;
     }
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < K; ++h)
-        if (rank[h] >= 0) recs[rank[h]] = o[h];
+        if (lane + 32 * h < nn) {
+            Rec4<float> o;
+            o.a = mine[h].c;
+            o.b = mine[h].d;
+            o.c = sqrtf(mine[h].a * mine[h].a + mine[h].b * mine[h].b);   // src/nb.c:440
+            o.d = lr_beta_sectors(mine[h].b, mine[h].a);
+            recs[rank[h]] = o;
+        }
     __syncwarp();
 }
 
@@ -861,16 +871,19 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     // from the back, so the coverage loop meets the wide ones first.  If more than kCertList qualify (dense packing,
     // explicit hydrogens), the bar is raised to caps at least 20, 35, 50 degrees wider, until they fit: the widest caps
     // are the ones that hide whole patches anyway.
-    const float bars[4] = {kCertCos, 0.84339145f, 0.67559021f, 0.46174861f};   // cos(12.5, 32.5, 47.5, 62.5 deg)
     constexpr float kWide = 0.65f;   // cos(49.5 deg); measured optimum on the 100k globule (0.5: 0.508 ms, 0.65: 0.467, 0.85: 0.484)
-#if FSB200_COMPACT_CERT
+    const float inv_2Ri = 0.5f / Ri;
+    // (The loops of this routine are deliberately NOT unrolled and use the approximate MUFU square root: it runs once per
+    //  atom, in warps that are all at different places of it, so its footprint in the instruction caches matters more than
+    //  its instruction count — ncu, round 2: half of the stall samples inside the unrolled version were `no_instruction`.
+    //  Every approximation is covered by the safety margin of the threshold below, 1e-5 d + 1e-6, ~80 ulp.)
 #pragma unroll 1
-#endif
     for (int attempt = 0; attempt < 4; ++attempt) {
-        const float bar = bars[attempt];
+        const float bar = attempt == 0 ? kCertCos : attempt == 1 ? 0.84339145f : attempt == 2 ? 0.67559021f : 0.46174861f;   // cos(12.5, 32.5, 47.5, 62.5 deg)
         int n_back = 0;
         n_useful = 0;
         if (attempt > 0) __syncwarp();                     // the list is rewritten by other lanes than in the last attempt
+#pragma unroll 1
         for (int base = 0; base < nn; base += 32) {
             const int j = base + lane;
             float4 e = make_float4(0.f, 0.f, 0.f, 3.0e38f);
@@ -879,13 +892,13 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
                 const Rec4<T> r = recs[j];
                 e.x = (float)r.a; e.y = (float)r.b; e.z = (float)r.c;
                 const float d2 = e.x * e.x + e.y * e.y + e.z * e.z;
-                const float d = sqrtf(d2);
-                const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) / (2.f * Ri);
+                const float d = fast_sqrt(d2);
+                const float t = HAS_T ? (float)r.d : (Ri * Ri + d2 - (float)r.d * (float)r.d) * inv_2Ri;
                 if (t < -d - 1e-4f * (d + Ri)) inside = true;  // sphere i lies strictly inside sphere a (coincident equal
                                                                // spheres, t = d = 0, do NOT count: the reference decides
                                                                // their points one rounding at a time)
                 else if (t < d * bar) {                        // cap wide enough for this attempt
-                    e.w = t * kCertCos + sqrtf(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
+                    e.w = t * kCertCos + fast_sqrt(fmaxf(d2 - t * t, 0.f)) * kCertSin + 1e-5f * d + 1e-6f;
                     useful = true;
                     wide = attempt > 0 || t < d * kWide;
                 }
@@ -906,18 +919,17 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     if (n_useful == 0 || n_useful > kCertList) return false;   // nothing to work with / too many for the short list
     __syncwarp();
     const float4 u0 = __ldg(dirs + lane), u1 = __ldg(dirs + lane + 32);   // two antipodal pairs per lane, L1-resident table
-    bool p0 = false, m0 = false, p1 = false, m1 = false;                  // patch of +u0, -u0, +u1, -u1 hidden
+    unsigned hidden = 0u;                                                 // bit 0..3: patch of +u0, -u0, +u1, -u1 hidden
     const float4 none = make_float4(0.f, 0.f, 0.f, 3.0e38f);
     // Phase 1 — lanes = directions, loop over the WIDE caps (front of the list): a dozen caps hide most of the sphere.
+#pragma unroll 1
     for (int j = 0; j < n_wide; j += 2) {
         const float4 e = list[j];
         const float4 f = j + 1 < n_wide ? list[j + 1] : none;
         const float e0 = fmaf(u0.x, e.x, fmaf(u0.y, e.y, u0.z * e.z)), e1 = fmaf(u1.x, e.x, fmaf(u1.y, e.y, u1.z * e.z));
         const float f0 = fmaf(u0.x, f.x, fmaf(u0.y, f.y, u0.z * f.z)), f1 = fmaf(u1.x, f.x, fmaf(u1.y, f.y, u1.z * f.z));
-        p0 = p0 || e0 >= e.w || f0 >= f.w;
-        m0 = m0 || -e0 >= e.w || -f0 >= f.w;
-        p1 = p1 || e1 >= e.w || f1 >= f.w;
-        m1 = m1 || -e1 >= e.w || -f1 >= f.w;
+        hidden |= ((e0 >= e.w || f0 >= f.w) ? 1u : 0u) | ((-e0 >= e.w || -f0 >= f.w) ? 2u : 0u) |
+                  ((e1 >= e.w || f1 >= f.w) ? 4u : 0u) | ((-e1 >= e.w || -f1 >= f.w) ? 8u : 0u);
     }
     // Phase 2 — roles swapped for the few directions still open: lanes = the remaining (narrower) caps, two per lane
     // in registers, one direction at a time (uniform table load), one vote each.  The first direction nobody hides ends
@@ -927,13 +939,9 @@ __device__ __forceinline__ bool certify_buried(const Rec4<T> *recs, float4 *list
     const float4 c1 = lane + 32 < n_back ? list[kCertList - 1 - (lane + 32)] : none;
     __syncwarp();                                              // the list's memory is reused by the integrators
     bool ok = true;
-#if FSB200_COMPACT_CERT
 #pragma unroll 1
-#else
-#pragma unroll
-#endif
     for (int q = 0; q < 4 && ok; ++q) {
-        unsigned open = __ballot_sync(kFull, !(q == 0 ? p0 : q == 1 ? m0 : q == 2 ? p1 : m1));
+        unsigned open = __ballot_sync(kFull, !((hidden >> q) & 1u));
         const float sign = (q & 1) ? -1.f : 1.f;
         while (open) {
             const int l = __ffs(open) - 1;
@@ -1050,7 +1058,8 @@ __device__ __forceinline__ void write_area(const Workspace &ws, const IntegrateA
         args.peer_out[idx / args.owner_slice][idx] = area;                     // to the GPU that owns this part of the result
     } else {
         args.out[idx] = area;
-        for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
+        if (area != 0.0 || !args.peer_skip_zero)
+            for (int q = 0; q < args.n_peer_out; ++q) args.peer_out[q][idx] = area;   // the all-gather, store by store (NVLink)
     }
 }
 
@@ -1261,7 +1270,7 @@ __device__ __forceinline__ int add_acq_rel(int *p, int v) { __threadfence_block(
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }   // global counters only
 
 // executed by one full warp: stage fill number `fill` into slot sl
-__device__ __forceinline__ void fill_slot(const Workspace &ws, const IntegrateArgs &args, int n_items, Slot *sl,
+__device__ __noinline__ void fill_slot(const Workspace &ws, const IntegrateArgs &args, int n_items, Slot *sl,
                                           double4 *tile, uint64_t *bar, int fill, int lane)
 {
     const int n_front = ws.counters[kCtrItems];
@@ -1553,6 +1562,21 @@ __device__ __noinline__ void redo_task(const Workspace &ws, const IntegrateArgs 
     __syncwarp();
 }
 
+// a task of k_slices: this lane's K records straight from the pool into registers, then the chunk
+template <int K>
+__device__ __forceinline__ double chunk_from_pool(const Rec4<float> *recs, KeyArc *arcs, const unsigned *marginal, int nn, double Ri,
+                                                  int ns, int s0, int s1, int lane)
+{
+    Rec4<float> r[K];
+    bool v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        v[k] = lane + 32 * k < nn;
+        r[k] = recs[v[k] ? lane + 32 * k : 0];
+    }
+    return lr_slices_chunk<K>(r, v, arcs, marginal, nn, Ri, ns, s0, s1, lane);
+}
+
 __global__ void __launch_bounds__(kSliceWarps * 32, FSB200_SLICE_CTAS) k_slices(Workspace ws, IntegrateArgs args)
 {
     __shared__ __align__(16) unsigned char mem_all[kSliceWarps][kRedoMaxNeighbours * (sizeof(Rec4<double>) + sizeof(Arc<double>))];
@@ -1579,15 +1603,22 @@ __global__ void __launch_bounds__(kSliceWarps * 32, FSB200_SLICE_CTAS) k_slices(
         const double Ri = h->Ri;
         const TodoLayout L = todo_layout(ns, nn);
         const Rec4<float> *recs = reinterpret_cast<const Rec4<float> *>(rec + L.recs);
-        Rec4<float> r[kLrK];
-        bool v[kLrK];
-#pragma unroll
-        for (int k = 0; k < kLrK; ++k) {
-            v[k] = lane + 32 * k < nn;
-            r[k] = recs[v[k] ? lane + 32 * k : 0];
-        }
         const unsigned *marginal = h->has_marginal ? reinterpret_cast<const unsigned *>(rec + L.marginal) : nullptr;
-        const double part = lr_slices_chunk<kLrK>(r, v, arcs, marginal, nn, Ri, ns, c * S, min(c * S + S, ns), lane);
+        // One instantiation of the slice loop per number of record groups: in this kernel (unlike the fused one, where a
+        // second instantiation cost more in instruction-cache misses than it saved) specialisation pays: C2 0.498 ms with
+        // K = 3 only, 0.474 with K = 2 added for the atoms with <= 64 neighbours (most atoms with exposed surface), 0.466
+        // with K = 1 as well.
+        double part;
+        const int s0 = c * S, s1 = min(c * S + S, ns);
+#if FSB200_SLICES_K >= 3
+        if (nn <= 32) part = chunk_from_pool<1>(recs, arcs, marginal, nn, Ri, ns, s0, s1, lane);
+        else
+#endif
+#if FSB200_SLICES_K >= 2
+        if (nn <= 64) part = chunk_from_pool<2>(recs, arcs, marginal, nn, Ri, ns, s0, s1, lane);
+        else
+#endif
+            part = chunk_from_pool<kLrK>(recs, arcs, marginal, nn, Ri, ns, s0, s1, lane);
         if (lane == 0) reinterpret_cast<double *>(rec + L.partial)[c] = part;
         __syncwarp();
     }

@@ -156,6 +156,13 @@ class PeerGather:
         self.windows = [o[slot[0]:slot[0] + slot[1]] if slot else o for o in self.outs]
         self.parity = 0
         self.out = self.outs[0]
+        # nine areas in ten are exactly 0 (buried atoms): they are not stored remotely; every rank zeroes the buffer of the
+        # NEXT step ahead of its barrier signal of this step instead (stream order makes the zeroing visible before any peer
+        # can pass that barrier and start writing into it)
+        for o in self.outs:
+            o.zero_()
+        torch.cuda.current_stream().synchronize()
+        engine.set_peer_zero_skipping(True)
         dist.barrier()
 
     def barrier(self):
@@ -168,6 +175,7 @@ class PeerGather:
         self.parity ^= 1
         off = 8 * int(self.slot[0]) if self.slot else 0
         self.engine.set_peer_outputs([p.ptr + off for r, p in enumerate(self.peers[k]) if r != self.rank])
+        self.outs[k ^ 1].zero_()   # the buffer of the next step (its last result has been consumed: step() was called again)
         enqueue(self.windows[k])
         self.barrier()          # every rank's kernels — and with them every peer store into my buffer — are complete
         rc = self.engine.finish()
@@ -182,6 +190,7 @@ class PeerGather:
 
     def close(self):
         self.engine.set_peer_outputs([])
+        self.engine.set_peer_zero_skipping(False)
         for k in range(2):
             for r, p in enumerate(self.peers[k]):
                 if r != self.rank:

@@ -175,6 +175,10 @@ int fsb200_ctx_finish(fsb200_ctx *ctx);
  * call writes the caller's atom order (not the sorted order), so after all shards have finished every buffer holds the
  * complete result and no unpermute / NCCL all-gather is needed.  n_peers = 0 switches it off. */
 int fsb200_ctx_set_peer_outputs(fsb200_ctx *ctx, int n_peers, double *const *d_peer_sasa);
+/* With zero skipping on, an area of exactly 0 (nine atoms in ten of a large structure: everything the buried-atom certificate
+ * settles) is NOT stored into the peer buffers: their owners zero them before the step (cudaMemsetAsync ahead of their
+ * barrier signal), which turns 8 B per atom and peer into 8 B per EXPOSED atom and peer. */
+int fsb200_ctx_set_peer_zero_skipping(fsb200_ctx *ctx, int on);
 /* CUDA IPC plumbing for the one-process-per-GPU case: allocate a device buffer that other processes can map, export its
  * 64-byte handle, map a peer's buffer, unmap it. */
 int fsb200_ipc_alloc(int device, unsigned long long bytes, void **d_ptr, unsigned char handle[64]);

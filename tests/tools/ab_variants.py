@@ -20,6 +20,8 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "product": [],
     "fused": ["env:FSB200_PIPELINE=fused"],            # the same library, everything inside k_integrate (round 1's layout)
+    "slices_k3only": ["FSB200_SLICES_K=1"],
+    "no_exact_slices": ["FSB200_EXACT_SLICES=0"],
     "r1_kernel": ["@integrate.cu=f4eaa4c"],          # integrate.cu of the round-1 commit, against today's api.cu / cells.cu
 }
 TAIL_VARIANTS = ("product",)   # these also measure the 1M-atom PDB-rounded error tail
