@@ -1,11 +1,10 @@
-// freesasa_b200/csrc/integrate.cu — the two surface integrators as ONE persistent sm_100a kernel template.
+// freesasa_b200/csrc/integrate.cu — the two surface integrators for sm_100a.
 //
-// Scheduling (details at k_integrate): every CTA keeps a ring of two shared-memory tiles.  A tile holds the
-// 27-cell neighbourhood of one work item (<= 16 atoms of one grid cell): 9 contiguous runs of the
-// cell-sorted atom array (x is the fastest cell coordinate), staged with TMA bulk copies
-// (cp.async.bulk + mbarrier, SASS UBLKCP).  The CTA's 14 warps are independent: each claims ONE atom at a
-// time with a compare-and-swap, and the warp that completes the last neighbour gather of a tile recycles it
-// from the global work queue while everybody else is already integrating.
+// k_integrate<ALG,T> is a persistent kernel (details at the kernel): every CTA keeps a ring of two shared-memory tiles.  A
+// tile holds the 27-cell neighbourhood of one work item (<= 16 atoms of one grid cell): 9 contiguous runs of the
+// cell-sorted atom array (x is the fastest cell coordinate), staged with TMA bulk copies (cp.async.bulk + mbarrier, SASS
+// UBLKCP).  The CTA's 14 warps are independent: each claims ONE atom at a time with a compare-and-swap, and the warp that
+// completes the last neighbour gather of a tile recycles it from the global work queue.
 //
 // Per atom, one warp:
 //   1. gather      filters the staged candidates with the reference's exact fp64 contact test
@@ -13,15 +12,21 @@
 //                  private shared-memory list in the atom-local frame (differences formed in fp64, then
 //                  rounded).  The neighbour SET equals the reference's, without its ~10 % duplicate entries
 //                  (forward-cell rule, src/nb.c:103-110) and without any global adjacency array.
-//   2. Lee & Richards (src/sasa_lr.c:270-408), lanes = neighbours:
-//        lr_atom_fastk<3>   fp32, <= 96 neighbours (the production path): z-sorted records in registers,
-//                           burial vote, sector-mask full-cover early-out, tiny exact merge of what is left
-//        lr_atom_fast       fp32, 97..kNbCap neighbours: all arcs of a slice merged pairwise with unique keys
-//        lr_atom<T>         generic (fp64 validation mode; fp32 in the global-memory overflow kernel)
-//      All three use the cancellation-free half-angle form tan^2(alpha/2) = (a+b-d)(d+b-a)/((d+a-b)(a+b+d))
+//   2. certificate tries to PROVE that the atom has no exposed surface (certify_buried): 9 atoms in 10 of a large
+//                  structure end here with area exactly 0, as in the reference.
+//   3. Lee & Richards (src/sasa_lr.c:270-408), lanes = neighbours.  fp32 production path = SPLIT PIPELINE: this kernel
+//      z-sorts and prepares the records (lr_prepare_sorted), marks the slices in which some pair of circles is within
+//      rounding distance of a tangency (lr_mark_marginal, closed form) and writes a task record; k_slices runs the slice
+//      loop (lr_slices_chunk: records in registers, one REDUX for burial / arcs, sector-mask full-cover early-out, exact
+//      sort-free merge of what is left) on chunks of slices from a queue and the marginal slices in fp64 (redo_task);
+//      k_finish adds the chunks in order.  Other paths, all inside k_integrate:
+//        lr_atom_fastk<3>   the same slice loop, chunk after chunk (pool full, or FSB200_PIPELINE=fused)
+//        lr_atom_fast       fp32, 97..kNbCap neighbours: all arcs of a slice merged pairwise
+//        lr_atom<T>         generic (fp64 mode, the fp64 redo, the global-memory overflow kernel)
+//      All use the cancellation-free half-angle form tan^2(alpha/2) = (a+b-d)(d+b-a)/((d+a-b)(a+b+d))
 //      instead of acos of a quotient (src/sasa_lr.c:335) and hoist beta = atan2(dy,dx)+pi out of the slice
 //      loop (the reference recomputes it per slice, :337).
-//   3. Shrake & Rupley (src/sasa_sr.c:276-338), lanes = test points (sr_atom): point u of atom i is hidden by
+//   4. Shrake & Rupley (src/sasa_sr.c:276-338), lanes = test points (sr_atom): point u of atom i is hidden by
 //      neighbour a iff u.D_a >= t_a, D_a = x_a - x_i, t_a = (Ri^2+|D_a|^2-Ra^2)/(2Ri) — algebraically the
 //      reference's |Ri u + x_i - x_a|^2 <= Ra^2.  3 FMA + compare per test in fp32; tests inside a rounding
 //      band are re-decided by replaying the reference's exact fp64 expression, so every inside/outside
@@ -836,8 +841,10 @@ __device__ __forceinline__ double sr_atom(Rec4<T> *recs, int *cidx, const double
 // Most atoms of a large structure have NO exposed surface (92 % of the 100k-atom benchmark globule), and
 // for them every slice ends "buried" or "fully covered" and every test point is hidden.  This routine proves
 // that outcome for a whole atom at once, at ~5 % of the cost of integrating it:
-//   * kCertPoints probe directions u_k (golden spiral) cover the unit sphere with patches of angular radius
-//     rho = 14.5 deg (measured covering radius 13.82 deg + probe-set resolution 0.25 deg, tests/test_certificate.py);
+//   * kCertPoints = 128 probe directions u_k — 64 antipodal pairs, Lloyd-relaxed under that symmetry (cert_dirs.inc,
+//     tests/golden/make_cert_directions.py) — cover the unit sphere with patches of angular radius rho = 12.5 deg:
+//     measured covering radius 12.17 deg (tests/test_certificate.py measures it from the library's own table and asserts
+//     it against kCertCos), i.e. a margin of 0.3 deg + the fp32 safety term of the threshold below;
 //   * neighbour a hides the cap of half-angle theta_a around D_a, cos(theta_a) = t_a/|D_a|,
 //     t_a = (Ri^2+|D_a|^2-Ra^2)/(2Ri); it hides the WHOLE patch k iff angle(u_k, D_a) <= theta_a - rho, i.e.
 //     u_k.D_a >= |D_a| cos(theta_a - rho) = t_a cos(rho) + sqrt(|D_a|^2 - t_a^2) sin(rho)  (=: t'_a, plus an
