@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -323,6 +324,80 @@ private:
     std::atomic<int> next_{0};
     int n_tasks_ = 0, active_ = 0, generation_ = 0;
 };
+
+// A host thread that is created once and then parked on a condition variable between jobs.  The multi-device entry point
+// and the overlapped batch path used to start fresh std::threads per call; a new thread pays for its CUDA thread state on
+// its first runtime call (cudaSetDevice: 0.1-1 ms), which on eight GPUs was most of a 3 ms call.
+class ParkedThread {
+public:
+    ~ParkedThread()
+    {
+        if (th_.joinable()) {
+            {
+                std::lock_guard<std::mutex> g(m_);
+                quit_ = true;
+            }
+            cv_.notify_all();
+            th_.join();
+        }
+    }
+    void start(std::function<void()> job)   // may throw std::system_error (no thread could be created)
+    {
+        if (!th_.joinable()) th_ = std::thread([this] { loop(); });
+        {
+            std::lock_guard<std::mutex> g(m_);
+            job_ = std::move(job);
+            pending_ = true;
+            done_ = false;
+        }
+        cv_.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return done_; });
+    }
+
+private:
+    void loop()
+    {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return pending_ || quit_; });
+                if (quit_) return;
+                job = std::move(job_);
+                pending_ = false;
+            }
+            try {
+                job();
+            } catch (...) {
+            }
+            {
+                std::lock_guard<std::mutex> g(m_);
+                done_ = true;
+            }
+            cv_.notify_all();
+        }
+    }
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::function<void()> job_;
+    bool pending_ = false, done_ = true, quit_ = false;
+};
+
+// worker d of the multi-device entry point (leaked on purpose: process exit must not wait for parked threads)
+ParkedThread &device_worker(int d)
+{
+    static ParkedThread *workers[FSB200_MAX_DEVICES] = {};
+    static std::mutex m;
+    std::lock_guard<std::mutex> g(m);
+    if (!workers[d]) workers[d] = new ParkedThread();
+    return *workers[d];
+}
+std::mutex g_multi_call_lock;   // one multi-device call at a time (it uses every device and every worker anyway)
 
 struct CopyJob {
     void *dst;
@@ -757,7 +832,11 @@ fsb200_ctx *fsb200_ctx_create(int device)
         return nullptr;
     }
     DeviceGuard guard(device);
-    fsb200_ctx *c = new fsb200_ctx();
+    fsb200_ctx *c = new (std::nothrow) fsb200_ctx();
+    if (!c) {
+        fail("out of host memory");
+        return nullptr;
+    }
     c->device = device;
     {   // FSB200_PIPELINE=fused: everything inside the one persistent kernel (round 1's layout; for A/B measurements)
         const char *env = getenv("FSB200_PIPELINE");
@@ -771,10 +850,10 @@ fsb200_ctx *fsb200_ctx_create(int device)
     for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_status, sizeof(int) * kCtrCount) == cudaSuccess;
     if (ok) {  // the certificate's probe set: kCertPairs antipodal pairs (cert_dirs.inc)
-        std::vector<float4> pf(kCertPairs);
+        float4 pf[kCertPairs];
         for (int k = 0; k < kCertPairs; ++k) pf[k] = make_float4(kCertDirs[k][0], kCertDirs[k][1], kCertDirs[k][2], 0.f);
-        ok = c->cert_points.ensure(pf.size()) == cudaSuccess &&
-             cudaMemcpy(c->cert_points.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = c->cert_points.ensure(kCertPairs) == cudaSuccess &&
+             cudaMemcpy(c->cert_points.p, pf, sizeof pf, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) {
         fail("could not initialise context on device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
@@ -827,8 +906,17 @@ int fsb200_ctx_stats(const fsb200_ctx *c, fsb200_stats *out)
     return FSB200_SUCCESS;
 }
 
+static int ctx_calc_batch_impl(fsb200_ctx *c, int alg, int n_struct, const int *n_atoms, const double *const *xyz,
+                               const double *const *radii, double *const *sasa, double probe, int resolution);
+
 int fsb200_ctx_calc_batch(fsb200_ctx *c, int alg, int n_struct, const int *n_atoms, const double *const *xyz,
                           const double *const *radii, double *const *sasa, double probe, int resolution)
+{
+    return guarded([&]() -> int { return ctx_calc_batch_impl(c, alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution); });
+}
+
+static int ctx_calc_batch_impl(fsb200_ctx *c, int alg, int n_struct, const int *n_atoms, const double *const *xyz,
+                               const double *const *radii, double *const *sasa, double probe, int resolution)
 {
     if (!c) return fail("null context");
     if (n_struct <= 0 || !n_atoms || !xyz || !radii || !sasa) return fail("invalid batch arguments");
@@ -931,6 +1019,7 @@ int fsb200_ctx_calc(fsb200_ctx *c, int alg, double *sasa, const double *xyz, con
 int fsb200_ctx_neighbour_counts(fsb200_ctx *c, int *counts, const double *xyz, const double *radii, int n, double probe)
 {
     if (!c || !counts || !xyz || !radii || n <= 0) return fail("invalid arguments");
+    return guarded([&]() -> int {
     std::lock_guard<std::mutex> g(c->lock);
     DeviceGuard guard(c->device);
     CU(c->in_xyz.ensure(3 * (size_t)n));
@@ -946,6 +1035,7 @@ int fsb200_ctx_neighbour_counts(fsb200_ctx *c, int *counts, const double *xyz, c
         return FSB200_SUCCESS;
     };
     return run_pipeline(c, rq, download);
+    });
 }
 
 static int device_request(fsb200_ctx *c, Request &rq, int alg, const double *d_xyz, const double *d_radii, int n_total,
@@ -1139,11 +1229,13 @@ int fsb200_cert_directions(double *out)
 int fsb200_test_points(int n_points, double *out)
 {
     if (n_points <= 0 || !out) return fail("invalid arguments");
-    std::vector<double> pd;
-    std::vector<float4> pf;
-    make_test_points(n_points, pd, pf);
-    std::memcpy(out, pd.data(), pd.size() * sizeof(double));
-    return FSB200_SUCCESS;
+    return guarded([&]() -> int {
+        std::vector<double> pd;
+        std::vector<float4> pf;
+        make_test_points(n_points, pd, pf);
+        std::memcpy(out, pd.data(), pd.size() * sizeof(double));
+        return FSB200_SUCCESS;
+    });
 }
 
 // ---- context-free drop-in entry points ------------------------------------------------------------------
@@ -1155,8 +1247,17 @@ int fsb200_test_points(int n_points, double *out)
 constexpr long long kOverlapMinAtoms = 400000;   // below this one pass is cheaper than a second thread
 constexpr long long kOverlapChunkAtoms = 320000; // sub-batch size: ~10 MB up, ~2.5 MB down, a few ms of kernel
 
+static int calc_batch_impl(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
+                           double *const *sasa, double probe, int resolution);
+
 int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
                       double *const *sasa, double probe, int resolution)
+{
+    return guarded([&]() -> int { return calc_batch_impl(alg, n_struct, n_atoms, xyz, radii, sasa, probe, resolution); });
+}
+
+static int calc_batch_impl(int alg, int n_struct, const int *n_atoms, const double *const *xyz, const double *const *radii,
+                           double *const *sasa, double probe, int resolution)
 {
     long long total = 0;
     if (n_struct > 0 && n_atoms)
@@ -1206,15 +1307,15 @@ int fsb200_calc_batch(int alg, int n_struct, const int *n_atoms, const double *c
             }
         }
     };
-    std::vector<std::thread> helpers;
+    static_assert(kMaxWorkers >= 2, "");
+    thread_local ParkedThread helper;   // n_workers == 2: this thread + one parked helper of its own
     const bool copy_inline = g_copy_inline;
-    for (int w = 1; w < n_workers; ++w)
-        helpers.emplace_back([&work, w, copy_inline] {
-            g_copy_inline = copy_inline;
-            work(w);
-        });
+    helper.start([&work, copy_inline] {
+        g_copy_inline = copy_inline;
+        work(1);
+    });
     work(0);
-    for (auto &h : helpers) h.join();
+    helper.wait();
     g_last_stats = ctx[0]->stats;   // the last sub-batch of worker 0; totals below
     g_last_stats.n_atoms = (int)total;
     g_last_stats.n_structures = n_struct;
@@ -1412,12 +1513,13 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
         }
     };
     {
-        std::vector<std::thread> helpers;
-        helpers.reserve(N);
+        std::lock_guard<std::mutex> one_call(g_multi_call_lock);
+        int started = 1;
         for (int d = 1; d < N; ++d) {
             try {
-                helpers.emplace_back(work, d);
-            } catch (...) {   // cannot start a helper thread: the call fails, but the started ones must not wait for it
+                device_worker(d).start([&work, d] { work(d); });
+                ++started;
+            } catch (...) {   // cannot start a worker thread: the call fails, but the started ones must not wait for it
                 failed.store(true);
                 rc[d] = FSB200_FAIL;
                 err[d] = "cannot start a host thread";
@@ -1426,7 +1528,7 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
             }
         }
         work(0);
-        for (auto &h : helpers) h.join();
+        for (int d = 1; d < started; ++d) device_worker(d).wait();
     }
     ms.total_ms = (float)ms_since(t_begin);
     ms.download_ms = ms.total_ms - ms.upload_ms - ms.compute_ms;
@@ -1489,13 +1591,24 @@ int multi_batch(int alg, int n_struct, const int *n_atoms, const double *const *
         if (d < FSB200_MAX_DEVICES) ms.device_ms[d] = (float)ms_since(t0);   // wall time of this device's share
     };
     {
-        std::vector<std::thread> helpers;
-        for (int d = 1; d < N; ++d) helpers.emplace_back(work, d);
+        std::lock_guard<std::mutex> one_call(g_multi_call_lock);
+        int started = 1;
+        bool all_started = true;
+        for (int d = 1; d < N && all_started; ++d) {
+            try {
+                device_worker(d).start([&work, d] { work(d); });
+                ++started;
+            } catch (...) {   // cannot start a worker thread: the shares of the started ones complete, the call fails
+                all_started = false;
+                rc[d] = FSB200_FAIL;
+                err[d] = "cannot start a host thread";
+            }
+        }
         const int prev = default_device();
-        work(0);
+        if (all_started) work(0);
         g_copy_inline = false;
         if (prev >= 0) cudaSetDevice(prev);
-        for (auto &h : helpers) h.join();
+        for (int d = 1; d < started; ++d) device_worker(d).wait();
     }
     ms.total_ms = (float)ms_since(t_begin);
     ms.compute_ms = ms.total_ms;
