@@ -132,6 +132,7 @@ struct fsb200_ctx {
     DevBuf<unsigned long long> todo_list;
     DevBuf<TodoCtl> todo_ctl;
     bool split_pipeline = true;
+    size_t pool_bytes_per_atom = 1024;   // FSB200_POOL_BYTES_PER_ATOM: test hook (a tiny pool forces the in-kernel fallback)
     // Shrake-Rupley test points of the last resolution used
     // probe directions of the buried-atom certificate (uploaded once per context)
     DevBuf<float4> cert_points;
@@ -527,7 +528,7 @@ int enqueue_pipeline(fsb200_ctx *c, const Request &rq)
         // largest record (96 neighbours); if a call needs more, the remaining atoms are integrated inside k_integrate with
         // the same arithmetic in the same order (bit-identical), only slower.
         const size_t owned = (size_t)(ws.shard_end - ws.shard_begin);
-        size_t bytes = owned * 1024 + (4u << 20);
+        size_t bytes = owned * c->pool_bytes_per_atom + (c->pool_bytes_per_atom == 1024 ? (4u << 20) : 4096);
         if (bytes > (16ull << 30)) bytes = 16ull << 30;
         CU(c->todo_pool.ensure(bytes));
         CU(c->todo_list.ensure(2 * (size_t)rq.n + 2));
@@ -841,6 +842,8 @@ fsb200_ctx *fsb200_ctx_create(int device)
     {   // FSB200_PIPELINE=fused: everything inside the one persistent kernel (round 1's layout; for A/B measurements)
         const char *env = getenv("FSB200_PIPELINE");
         if (env && strcmp(env, "fused") == 0) c->split_pipeline = false;
+        const char *pool = getenv("FSB200_POOL_BYTES_PER_ATOM");
+        if (pool && atoi(pool) > 0) c->pool_bytes_per_atom = (size_t)atoi(pool);
     }
     {   // FSB200_PRECISION=fp64: the drop-in entry points (which have no precision argument) use the all-fp64 kernels
         const char *env = getenv("FSB200_PRECISION");

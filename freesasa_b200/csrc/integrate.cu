@@ -621,6 +621,15 @@ constexpr int kLrK = 3;   // at most 32 K = 96 neighbours in registers
 __host__ __device__ inline int lr_chunk_slices(int ns) { return ns <= 64 * FSB200_CHUNK ? FSB200_CHUNK : (ns + 63) / 64; }   // at most 64 chunks per atom
 __host__ __device__ inline int lr_n_chunks(int ns) { return (ns + lr_chunk_slices(ns) - 1) / lr_chunk_slices(ns); }
 
+// area = delta Ri (exposed angle) (src/sasa_lr.c:360) from the fp32 path's angle in sectors (2 pi / 32 radians each) plus the
+// fp64 redo's contribution.  ONE definition with explicit roundings (no FMA contraction), used by the split pipeline
+// (k_finish) and by the fused path alike, so that an atom has the same bits whichever way it was computed.
+__device__ __forceinline__ double lr_area(double Ri, int ns, double sectors, double extra)
+{
+    const double delta = 2.0 * Ri / ns;
+    return __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, Ri), sectors), 0.19634954084936207), extra);
+}
+
 template <int K>
 __device__ __forceinline__ double lr_slices_chunk(const Rec4<float> (&r)[K], const bool (&v)[K], KeyArc *arcs,
                                                   const unsigned *marginal, int nn, double Ri_d, int ns, int s_begin, int s_end,
@@ -735,7 +744,7 @@ __device__ __forceinline__ double lr_atom_fastk(const Rec4<float> *recs, KeyArc 
     const int S = lr_chunk_slices(ns);
     double sum = 0.0;
     for (int s0 = 0; s0 < ns; s0 += S) sum += lr_slices_chunk<K>(r, v, arcs, marginal, nn, Ri_d, ns, s0, min(s0 + S, ns), lane);
-    return (2.0 * Ri_d / ns) * Ri_d * sum * 0.19634954084936207;   // sectors -> radians (2 pi / 32)
+    return sum;                                            // exposed angle in SECTORS: lr_area() turns it into an area
 }
 
 // ---- step 3: Shrake & Rupley ---------------------------------------------------------------------
@@ -1160,13 +1169,15 @@ __device__ __forceinline__ bool finish_atom(const Workspace &ws, const Integrate
                         return false;                               // k_slices (and k_redo) finish this atom
                     }
                     if (lane == 0 && args.todo_pool != nullptr) atomicAdd(&args.todo_ctl->n_inline, 1);
-                    area = lr_atom_fastk<3>(recs, arcs, can_redo ? reinterpret_cast<const unsigned *>(side) : nullptr, nn, s.R,
-                                            args.resolution, lane);
+                    const double sectors = lr_atom_fastk<3>(recs, arcs, can_redo ? reinterpret_cast<const unsigned *>(side) : nullptr,
+                                                            nn, s.R, args.resolution, lane);
+                    double extra = 0.0;
                     if (can_redo && __any_sync(kFull, side[lane] != 0)) {
                         if (lane == 0) atomicAdd(ws.counters + kCtrMarginal, 1);
-                        area += lr_redo_exact(ws.atoms, reinterpret_cast<unsigned char *>(wm.recs), wm.cidx, nn, s.x, s.y, s.z,
+                        extra = lr_redo_exact(ws.atoms, reinterpret_cast<unsigned char *>(wm.recs), wm.cidx, nn, s.x, s.y, s.z,
                                               s.R, args.resolution, lane);
                     }
+                    area = lr_area(s.R, args.resolution, sectors, extra);
                 } else {
                     lr_prepare<float>(recs, nn, lane);
                     area = lr_atom_fast(recs, arcs, nn, s.R, args.resolution, lane);
@@ -1641,9 +1652,7 @@ __global__ void __launch_bounds__(256) k_finish(Workspace ws, IntegrateArgs args
         const double *partial = reinterpret_cast<const double *>(rec + todo_layout(ns, h->nn).partial);
         double sum = 0.0;
         for (int k = 0; k < n_chunks; ++k) sum += partial[k];
-        const double Ri = h->Ri, delta = 2.0 * Ri / ns;
-        // fp32 path: sectors -> radians (2 pi / 32); the fp64 redo returns delta * Ri * angle itself
-        write_area(ws, args, h->pos, delta * Ri * sum * 0.19634954084936207 + h->extra);
+        write_area(ws, args, h->pos, lr_area(h->Ri, ns, sum, h->extra));   // the fp64 redo returns delta * Ri * angle itself
     }
 }
 

@@ -470,3 +470,35 @@ def test_one_million_atoms_pdb_rounded_low_resolution(eng32):
         got = eng32.calc(fs.LEE_RICHARDS, x, r, 1.4, slices)
         want = ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, slices)
         assert maxerr(got, want) < LR_TOL_TAIL, slices
+
+
+def test_full_task_pool_falls_back_bit_identically():
+    """The split pipeline keeps one task record per atom that has to be integrated in a pool sized for about half of the
+    atoms; an atom that does not fit is integrated inside k_integrate, chunk by chunk in the same order.  With the pool
+    shrunk to a few records (test hook) and with the pipeline fused, the areas must have the same bits as the normal run."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import numpy as np, freesasa_b200 as fs\n"
+            "x, r = fs.workloads.globule(30000, seed=21)\n"
+            "x, r = np.round(x, 3), np.round(r, 2)\n"
+            "e = fs.Engine(0)\n"
+            "a = e.calc(fs.LEE_RICHARDS, x, r, 1.4, 37)\n"
+            "e.set_certificate(False)\n"
+            "b = e.calc(fs.LEE_RICHARDS, x, r, 1.4, 37)\n"
+            "np.save(__import__('sys').argv[1], np.stack([a, b]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("normal", {}), ("tiny_pool", {"FSB200_POOL_BYTES_PER_ATOM": "16"}), ("fused", {"FSB200_PIPELINE": "fused"})):
+        path = os.path.join(root, "gpurun_out", f"_pool_{name}.npy")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, PYTHONPATH=root, **env), check=True)
+        outs[name] = np.load(path)
+        os.remove(path)
+    np.testing.assert_array_equal(outs["normal"][0], outs["normal"][1])      # certificate on / off
+    np.testing.assert_array_equal(outs["normal"], outs["tiny_pool"])         # pool full: in-kernel fallback
+    np.testing.assert_array_equal(outs["normal"], outs["fused"])             # everything in one kernel
+    x, r = fs.workloads.globule(30000, seed=21)
+    x, r = np.round(x, 3), np.round(r, 2)
+    assert maxerr(outs["normal"][0], ob.oracle_calc(x, r, ob.LEE_RICHARDS, 1.4, 37)) < LR_TOL_TAIL
