@@ -25,10 +25,10 @@ namespace fsb200 {
 // Build-time experiment knobs.  The defaults ARE the product; tests/tools/ab_variants.py builds variants side by side
 // (libfsb200_<name>.so) to measure one change at a time on the GPU box.
 #ifndef FSB200_WARPS
-#define FSB200_WARPS 14
+#define FSB200_WARPS 14           // warps per CTA of k_integrate (16 at a 64-register cap: slower)
 #endif
 #ifndef FSB200_FUSED_VOTES
-#define FSB200_FUSED_VOTES 1      // slice loop: one REDUX.OR instead of 2 + K votes
+#define FSB200_FUSED_VOTES 1      // slice loop: one REDUX.OR instead of 1 + K votes (same speed within 1 %)
 #endif
 #ifndef FSB200_EXACT_SLICES
 #define FSB200_EXACT_SLICES 1     // fp32 L&R: slices with a near-tangent circle pair are redone in fp64
@@ -44,10 +44,10 @@ namespace fsb200 {
 #define FSB200_RING_ATOMICS 1     // ring protocol through acquire/release atomics (0: round 1's volatile polls, for A/B timing)
 #endif
 #ifndef FSB200_SPLIT
-#define FSB200_SPLIT 1            // fp32 L&R: k_integrate prepares, k_slices integrates chunks of slices, k_redo the marginal ones
+#define FSB200_SPLIT 1            // fp32 L&R: k_integrate prepares, k_slices integrates chunks of slices (and the marginal ones in fp64), k_finish sums
 #endif
 #ifndef FSB200_CHUNK
-#define FSB200_CHUNK 16           // slices per task of k_slices (8: 0.523 ms, 16: 0.517 ms on C2; 4: slower)
+#define FSB200_CHUNK 16           // slices per task of k_slices (C2: 8: 0.523 ms, 16: 0.517 ms; 4: slower)
 #endif
 #ifndef FSB200_SLICE_CTAS
 #define FSB200_SLICE_CTAS 4       // CTAs of k_slices per SM the compiler has to make room for (register cap)
@@ -56,16 +56,10 @@ namespace fsb200 {
 #define FSB200_SLICES_K 3          // k_slices: instantiations of the slice loop by record groups: 1 = K 3 only; 2 = K 2 + 3; 3 = K 1 + 2 + 3
 #endif
 #ifndef FSB200_RING_SLOTS
-#define FSB200_RING_SLOTS 2
+#define FSB200_RING_SLOTS 2        // tiles in flight per CTA (3 x 512-atom tiles: no gain; 4 x 384: slower)
 #endif
 #ifndef FSB200_TILE_CAP
-#define FSB200_TILE_CAP 640
-#endif
-#ifndef FSB200_PIN_LANE
-#define FSB200_PIN_LANE 0
-#endif
-#ifndef FSB200_COMPACT_CERT
-#define FSB200_COMPACT_CERT 0     // certificate: do not unroll the retry / open-direction loops (smaller SASS)
+#define FSB200_TILE_CAP 640        // atoms per tile; larger neighbourhoods are read from global memory
 #endif
 
 constexpr int kWarpsPerCta = FSB200_WARPS;  // warps claim atoms dynamically from the CTA's ring of staged tiles
@@ -150,7 +144,7 @@ struct TodoCtl {
     int n_todo;                     // task records written by k_integrate
     int task_head;                  // queue head of k_slices: task = (record, chunk of slices)
     int n_redo;                     // records with marginal slices (fp64 redo tasks, the first tasks of k_slices)
-    int redo_head;                  // unused
+    int reserved;
     int n_inline;                   // atoms integrated inside k_integrate because the pool was full
     int pad;
 };

@@ -641,7 +641,7 @@ __device__ __forceinline__ double lr_slices_chunk(const Rec4<float> (&r)[K], con
     double acc = 0.0;                                      // exposed angle in sectors
 
     for (int s = s_begin; s < s_end; ++s) {
-#if FSB200_EXACT_SLICES && !defined(FSB200_DBG_NO_BITTEST)
+#if FSB200_EXACT_SLICES
         if (marginal && ((marginal[s >> 5] >> (s & 31)) & 1u)) continue;   // redone in fp64 (one uniform load)
 #endif
         // slice centre relative to the atom centre (src/sasa_lr.c:305-307), formed in fp64 and rounded ONCE: a two-float
@@ -1358,13 +1358,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_integrate(Workspace ws, Inte
     __shared__ Slot slots[kRingSlots];
     __shared__ int cur;
 
-#if FSB200_PIN_LANE
-    const int tid = threadIdx.x, warp = tid >> 5;
-    int lane;   // opaque to the optimiser: kept in a register instead of being re-derived (S2R + LOP) all over the loops
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-#else
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#endif
     double4 *tiles = reinterpret_cast<double4 *>(smem);
     unsigned char *warp_mem = smem + (size_t)kRingSlots * kTileCap * sizeof(double4) + (size_t)warp * WarpLayout<ALG, T>::bytes(kNbCap);
     const WarpMem<ALG, T> wm(warp_mem, kNbCap);
