@@ -87,3 +87,18 @@ def test_structure_example_runs(tmp_path):
     written = [ln for ln in open(out_pdb).read().splitlines() if ln.startswith("ATOM")]
     assert len(written) == s.n
     assert [ln[60:66] for ln in written] == ["%6.2f" % v for v in sasa]
+
+
+def test_multi_gpu_example_compiles_and_links(tmp_path):
+    """examples/example_multi.c: fsb200_lr_multi() + fsb200_get_multi_stats() straight from C, engine library only."""
+    import __graft_entry__ as g
+
+    g.build()
+    csrc = os.path.join(ROOT, "freesasa_b200", "csrc")
+    exe = os.path.join(tmp_path, "example_multi")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=gnu99", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "example_multi.c"), "-L", csrc, "-lfsb200", f"-Wl,-rpath,{csrc}", "-lm", "-o", exe],
+                   check=True)
+    assert os.path.exists(exe)
+
