@@ -1485,7 +1485,7 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
         }
         if (d == 0) ms.upload_ms = (float)ms_since(t_begin);
         if (!failed.load()) {
-            // phase 3: cell list (replicated) + my share of the atoms; areas go straight to device 0 (peer stores)
+            // phase 3: cell list (replicated) + my share of the atoms; every area goes straight to its owner (peer stores)
             Range r("fsb200:multi:integrate_shard");
             // the result is partitioned by caller index: owner o holds [o * slice, (o + 1) * slice); its buffer is addressed
             // through a base shifted by -o * slice so that the kernel can index every owner's buffer with the caller index
@@ -1500,7 +1500,6 @@ int multi_replicated(int alg, int n, const double *xyz, const double *radii, dou
             if (rc[d] == FSB200_SUCCESS && d < FSB200_MAX_DEVICES) {
                 ms.integrate_ms[d] = c->stats.integrate_ms;
                 ms.device_ms[d] = c->stats.device_ms;
-                ms.n_certified += 0;
             }
         }
         barrier.wait();   // every shard has delivered its areas to their owners
